@@ -1,0 +1,470 @@
+// C ABI of cpflow_b200 (include/cpflow_b200.h).  Plain pointers and sizes; no exceptions cross
+// the boundary.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "cpflow_b200.h"
+#include "launch.cuh"
+#include "program.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(const char* what, cudaError_t e) {
+  return fail(CPF_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CPF_CUDA(call)                                        \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return cuda_fail(#call, e__);     \
+  } while (0)
+
+// per-device copy of the schedule and gate metadata, created on first use
+int device_program(const cpf::Program* prog, cpf::DeviceProgram* out) {
+  int dev = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(prog->mu);
+  auto it = prog->dev.find(dev);
+  if (it != prog->dev.end()) { *out = it->second; return CPF_OK; }
+  cpf::DeviceProgram d;
+  const size_t ns = prog->sched.size() * sizeof(uint32_t);
+  const size_t nu = prog->su2.size() * sizeof(cpf::Su2Meta);
+  const size_t nc = prog->cp.size() * sizeof(cpf::CpMeta);
+  CPF_CUDA(cudaMalloc(&d.sched, ns ? ns : 4));
+  CPF_CUDA(cudaMalloc(&d.su2, nu ? nu : 4));
+  CPF_CUDA(cudaMalloc(&d.cp, nc ? nc : 4));
+  if (ns) CPF_CUDA(cudaMemcpy(d.sched, prog->sched.data(), ns, cudaMemcpyHostToDevice));
+  if (nu) CPF_CUDA(cudaMemcpy(d.su2, prog->su2.data(), nu, cudaMemcpyHostToDevice));
+  if (nc) CPF_CUDA(cudaMemcpy(d.cp, prog->cp.data(), nc, cudaMemcpyHostToDevice));
+  prog->dev[dev] = d;
+  *out = d;
+  return CPF_OK;
+}
+
+template <typename R>
+int fill_common(const cpf::Program* prog, cpf::KParams<R>& p, int64_t batch) {
+  std::memset(&p, 0, sizeof(p));
+  cpf::DeviceProgram d;
+  int rc = device_program(prog, &d);
+  if (rc) return rc;
+  p.sched = d.sched; p.n_sched = (int)prog->sched.size();
+  p.su2 = d.su2; p.n_su2 = (int)prog->su2.size();
+  p.cp = d.cp; p.n_cp = (int)prog->cp.size();
+  p.P = prog->n_params; p.B = batch;
+  p.pen.kind = CPF_PEN_NONE;
+  p.nsteps = 1;
+  return CPF_OK;
+}
+
+template <typename R>
+int fill_penalty(const cpf::Program* prog, const cpf_penalty_spec* pen, cpf::KParams<R>& p,
+                 uint8_t** cp_pen_dev, cudaStream_t st) {
+  *cp_pen_dev = nullptr;
+  if (!pen || pen->kind == CPF_PEN_NONE) return CPF_OK;
+  if (pen->kind != CPF_PEN_PIECEWISE && pen->kind != CPF_PEN_L1)
+    return fail(CPF_ERR_INVALID, "unknown penalty kind");
+  if (pen->kind == CPF_PEN_PIECEWISE && (pen->n_segments < 1 || pen->n_segments > CPF_MAX_SEGMENTS))
+    return fail(CPF_ERR_INVALID, "penalty n_segments out of range");
+  if (pen->kind == CPF_PEN_PIECEWISE && !(pen->period > 0))
+    return fail(CPF_ERR_INVALID, "penalty period must be positive");
+  p.pen.kind = pen->kind; p.pen.nseg = pen->n_segments;
+  p.pen.r = (R)pen->r; p.pen.period = (R)pen->period;
+  for (int s = 0; s < pen->n_segments && s < CPF_MAX_SEGMENTS; ++s) {
+    p.pen.lo[s] = (R)pen->lo[s]; p.pen.hi[s] = (R)pen->hi[s];
+    p.pen.slope[s] = (R)pen->slope[s]; p.pen.icpt[s] = (R)pen->intercept[s];
+  }
+  if (pen->cp_mask) {
+    // only parameters of CP gates may be penalised
+    for (int i = 0; i < prog->n_params; ++i)
+      if (pen->cp_mask[i] && !prog->is_cp_param[i])
+        return fail(CPF_ERR_UNSUPPORTED, "cp_mask selects a parameter that does not feed a CP gate");
+    std::string flags(prog->cp.size(), '\0');
+    for (size_t k = 0; k < prog->cp.size(); ++k)
+      flags[k] = prog->cp[k].pidx >= 0 && pen->cp_mask[prog->cp[k].pidx] ? 1 : 0;
+    if (!flags.empty()) {
+      CPF_CUDA(cudaMallocAsync((void**)cp_pen_dev, flags.size(), st));
+      // pageable source: the runtime stages the bytes before returning, so `flags` may die
+      CPF_CUDA(cudaMemcpyAsync(*cp_pen_dev, flags.data(), flags.size(), cudaMemcpyHostToDevice, st));
+      p.cp_pen = *cp_pen_dev;
+    }
+  }
+  return CPF_OK;
+}
+
+template <typename R>
+int stage_target(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams<R>& p, bool single,
+                 R** packed, cudaStream_t st) {
+  const int cpt = single ? 1 : cpf::cpt_for<R>(prog->n_qubits);
+  const int words = cpf::target_words<R>(prog->n_qubits, cpt, single);
+  const size_t bytes = ((size_t)words * sizeof(R) + 15) & ~(size_t)15;
+  CPF_CUDA(cudaMallocAsync((void**)packed, bytes, st));
+  if (bytes != (size_t)words * sizeof(R)) CPF_CUDA(cudaMemsetAsync(*packed, 0, bytes, st));
+  int rc = cpf::launch_pack_target<R>((const R*)loss->target, *packed, prog->n_qubits, cpt, single, st);
+  if (rc) return fail(rc, "pack_target launch failed");
+  p.target_packed = *packed;
+  p.target_bytes = (int)bytes;
+  p.loss_kind = loss->kind;
+  return CPF_OK;
+}
+
+int check_loss(const cpf_loss_spec* loss) {
+  if (!loss || !loss->target) return fail(CPF_ERR_INVALID, "loss spec / target is NULL");
+  if (loss->kind < CPF_LOSS_HS || loss->kind > CPF_LOSS_RELPHASE)
+    return fail(CPF_ERR_INVALID, "unknown loss kind");
+  return CPF_OK;
+}
+
+template <typename R>
+int run_unitary(const cpf::Program* prog, int64_t batch, const void* angles, void* u_out, cudaStream_t st) {
+  cpf::KParams<R> p;
+  int rc = fill_common(prog, p, batch);
+  if (rc) return rc;
+  p.mode = cpf::M_UNITARY;
+  p.angles = (R*)angles; p.u_out = (R*)u_out;
+  std::string err;
+  rc = cpf::launch_engine<R>(p, prog->n_qubits, false, st, err);
+  return rc ? fail(rc, err) : CPF_OK;
+}
+
+template <typename R>
+int run_loss_grad(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf_penalty_spec* pen,
+                  int64_t batch, const void* angles, void* loss_out, void* reg_out, void* grad_out,
+                  cudaStream_t st) {
+  cpf::KParams<R> p;
+  int rc = fill_common(prog, p, batch);
+  if (rc) return rc;
+  const bool single = loss->kind == CPF_LOSS_STATE;
+  p.mode = cpf::M_LOSSGRAD;
+  p.angles = (R*)angles; p.loss_out = (R*)loss_out; p.reg_out = (R*)reg_out; p.grad_out = (R*)grad_out;
+  uint8_t* cp_pen = nullptr; R* packed = nullptr;
+  rc = fill_penalty(prog, pen, p, &cp_pen, st);
+  if (!rc) rc = stage_target(prog, loss, p, single, &packed, st);
+  if (!rc && grad_out) {
+    cudaError_t e = cudaMemsetAsync(grad_out, 0, (size_t)batch * prog->n_params * sizeof(R), st);
+    if (e != cudaSuccess) rc = cuda_fail("cudaMemsetAsync(grad)", e);
+  }
+  std::string err;
+  if (!rc) { rc = cpf::launch_engine<R>(p, prog->n_qubits, single, st, err); if (rc) fail(rc, err); }
+  if (packed) cudaFreeAsync(packed, st);
+  if (cp_pen) cudaFreeAsync(cp_pen, st);
+  return rc;
+}
+
+template <typename R>
+int run_cotangent(const cpf::Program* prog, int64_t batch, const void* angles, const void* cot,
+                  void* grad_out, cudaStream_t st) {
+  cpf::KParams<R> p;
+  int rc = fill_common(prog, p, batch);
+  if (rc) return rc;
+  p.mode = cpf::M_COTANGENT;
+  p.angles = (R*)angles; p.cot = (const R*)cot; p.grad_out = (R*)grad_out;
+  CPF_CUDA(cudaMemsetAsync(grad_out, 0, (size_t)batch * prog->n_params * sizeof(R), st));
+  std::string err;
+  rc = cpf::launch_engine<R>(p, prog->n_qubits, false, st, err);
+  return rc ? fail(rc, err) : CPF_OK;
+}
+
+template <typename R>
+int run_adam(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf_penalty_spec* pen,
+             const cpf_adam_spec* adam, int64_t batch, int64_t step0, int64_t num_steps,
+             const cpf_adam_buffers* buf, cudaStream_t st) {
+  cpf::KParams<R> p;
+  int rc = fill_common(prog, p, batch);
+  if (rc) return rc;
+  const bool single = loss->kind == CPF_LOSS_STATE;
+  p.mode = cpf::M_ADAM;
+  p.lr = (R)adam->lr; p.b1 = (R)adam->b1; p.b2 = (R)adam->b2; p.eps = (R)adam->eps;
+  p.omb1 = (R)(1.0 - adam->b1); p.omb2 = (R)(1.0 - adam->b2);
+  p.step0 = step0; p.nsteps = (int)num_steps;
+  p.angles = (R*)buf->angles; p.m = (R*)buf->m; p.v = (R*)buf->v; p.freeze = buf->freeze;
+  p.best_params = (R*)buf->best_params; p.best_regloss = (R*)buf->best_regloss;
+  p.best_reg = (R*)buf->best_reg; p.init_regloss = (R*)buf->init_regloss; p.init_reg = (R*)buf->init_reg;
+  p.hist_params = (R*)buf->hist_params; p.hist_regloss = (R*)buf->hist_regloss; p.hist_len = buf->hist_len;
+  uint8_t* cp_pen = nullptr; R* packed = nullptr;
+  rc = fill_penalty(prog, pen, p, &cp_pen, st);
+  if (!rc) rc = stage_target(prog, loss, p, single, &packed, st);
+  std::string err;
+  if (!rc) { rc = cpf::launch_engine<R>(p, prog->n_qubits, single, st, err); if (rc) fail(rc, err); }
+  if (packed) cudaFreeAsync(packed, st);
+  if (cp_pen) cudaFreeAsync(cp_pen, st);
+  return rc;
+}
+
+// ---- count_cz / projection (cp_utils.py:45-77, 111-141) ----
+template <typename R>
+__global__ void count_cz_kernel(const cpf::CpMeta* cp, int n_cp, int P, long long B, const R* angles,
+                                R threshold, int32_t* cz_out, R* projected, uint8_t* frozen) {
+  const long long b = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (b >= B) return;
+  const R two_pi = R(2.0 * M_PI), pi = R(M_PI);
+  if (projected)
+    for (int i = threadIdx.x; i < P; i += 32) projected[b * P + i] = angles[b * P + i];
+  if (frozen)
+    for (int i = threadIdx.x; i < P; i += 32) frozen[b * P + i] = 0;
+  __syncwarp();
+  int cz = 0;
+  for (int k = threadIdx.x; k < n_cp; k += 32) {
+    const int pidx = cp[k].pidx;
+    if (pidx < 0) continue;
+    const R a0 = angles[b * P + pidx];
+    const R a = cpf::pymod(a0, two_pi);
+    int val = 2;
+    if (a < threshold || cpf::abs_r(a - two_pi) < threshold) val = 0;
+    else if (cpf::abs_r(a - pi) < threshold) val = 1;
+    cz += val;
+    // project_cp_angle tests pi first, then 0 / 2pi (cp_utils.py:70-77)
+    int proj = -1;
+    if (cpf::abs_r(a - pi) < threshold) proj = 1;
+    else if (cpf::abs_r(a) < threshold || cpf::abs_r(a - two_pi) < threshold) proj = 0;
+    if (proj >= 0) {
+      if (projected) projected[b * P + pidx] = proj ? pi : R(0);
+      if (frozen) frozen[b * P + pidx] = 1;
+    }
+  }
+  for (int m = 16; m >= 1; m >>= 1) cz += __shfl_xor_sync(0xffffffffu, cz, m);
+  if (threadIdx.x == 0 && cz_out) cz_out[b] = cz;
+}
+
+// ---- jax 0.3.x threefry initial angles (main.py:541-548, cp_utils.py:13-42) ----
+__host__ __device__ inline void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  const int rot[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0]; x1 += ks[1];
+  for (int g = 0; g < 5; ++g) {
+    for (int r = 0; r < 4; ++r) {
+      x0 += x1;
+      const int s = rot[g & 1][r];
+      x1 = (x1 << s) | (x1 >> (32 - s));
+      x1 ^= x0;
+    }
+    x0 += ks[(g + 1) % 3];
+    x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+  }
+}
+// element i of jax's threefry_2x32(key, iota(n)): the count array is split in two halves
+__host__ __device__ inline uint32_t threefry_iota(uint32_t k0, uint32_t k1, uint32_t n, uint32_t i) {
+  const uint32_t h = (n + 1) / 2;  // odd n is padded with one zero
+  uint32_t x0, x1;
+  if (i < h) {
+    x0 = i; x1 = (h + i < n) ? h + i : 0u;
+    threefry2x32(k0, k1, x0, x1);
+    return x0;
+  }
+  x0 = i - h; x1 = i;
+  threefry2x32(k0, k1, x0, x1);
+  return x1;
+}
+
+template <typename R>
+__global__ void initial_angles_kernel(const cpf::CpMeta* cp, int n_cp, int P, uint32_t seed_hi,
+                                      uint32_t seed_lo, long long total, long long first,
+                                      long long count, int cp_dist, R* out) {
+  const long long s = (long long)blockIdx.x;
+  if (s >= count) return;
+  const long long g = first + s;
+  __shared__ uint32_t sub[2];
+  if (threadIdx.x == 0) {
+    // key, *subkeys = split(PRNGKey(seed), total + 1); sample g uses subkeys[g] = row g + 1
+    const uint32_t n1 = (uint32_t)(2 * (total + 1));
+    const uint32_t r = (uint32_t)(g + 1);
+    const uint32_t a0 = threefry_iota(seed_hi, seed_lo, n1, 2 * r);
+    const uint32_t a1 = threefry_iota(seed_hi, seed_lo, n1, 2 * r + 1);
+    // key, subkey = split(k): subkey is row 1 of a (2,2) split (cp_utils.py:31)
+    sub[0] = threefry_iota(a0, a1, 4, 2);
+    sub[1] = threefry_iota(a0, a1, 4, 3);
+  }
+  __syncthreads();
+  const float two_pi = 6.2831855f;  // float32(2*pi)
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const uint32_t bits = threefry_iota(sub[0], sub[1], (uint32_t)P, (uint32_t)i);
+    const float f = __uint_as_float((bits >> 9) | 0x3f800000u) - 1.0f;
+    float a = fmaxf(0.0f, __fadd_rn(__fmul_rn(f, two_pi), 0.0f));
+    out[s * P + i] = (R)a;
+  }
+  if (cp_dist == 1) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_cp; k += blockDim.x)
+      if (cp[k].pidx >= 0) out[s * P + cp[k].pidx] = R(0);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpf_version(void) { return CPF_VERSION; }
+const char* cpf_last_error(void) { return g_err.c_str(); }
+
+int cpf_program_create(int32_t n_qubits, int32_t n_ops, const cpf_op* ops, int32_t n_params,
+                       cpf_program** out) {
+  if (!out) return fail(CPF_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_ops < 0 || n_params < 0 || (n_ops > 0 && !ops)) return fail(CPF_ERR_INVALID, "bad ops / sizes");
+  cpf::Program* p = new (std::nothrow) cpf::Program();
+  if (!p) return fail(CPF_ERR_NOMEM, "out of memory");
+  try {
+    p->n_qubits = n_qubits; p->n_params = n_params;
+    p->ops.assign(ops, ops + n_ops);
+    std::string err = cpf::compile_program(*p);
+    if (!err.empty()) {
+      delete p;
+      return fail(n_qubits > CPF_MAX_QUBITS ? CPF_ERR_UNSUPPORTED : CPF_ERR_INVALID, err);
+    }
+  } catch (const std::exception& e) {
+    delete p;
+    return fail(CPF_ERR_NOMEM, e.what());
+  }
+  *out = reinterpret_cast<cpf_program*>(p);
+  return CPF_OK;
+}
+
+int cpf_program_destroy(cpf_program* prog) {
+  if (!prog) return CPF_OK;
+  cpf::Program* p = reinterpret_cast<cpf::Program*>(prog);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : p->dev) {
+    cudaSetDevice(kv.first);
+    cudaFree(kv.second.sched); cudaFree(kv.second.su2); cudaFree(kv.second.cp);
+  }
+  cudaSetDevice(cur);
+  delete p;
+  return CPF_OK;
+}
+
+int cpf_program_get_info(const cpf_program* prog, cpf_program_info* info) {
+  if (!prog || !info) return fail(CPF_ERR_INVALID, "NULL argument");
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  info->n_qubits = p->n_qubits; info->n_params = p->n_params; info->n_ops = (int)p->ops.size();
+  info->n_rotations = p->n_rot; info->n_phase = p->n_phase; info->n_fused = (int)p->su2.size();
+  info->n_sched = (int)p->sched.size(); info->reserved = 0;
+  return CPF_OK;
+}
+
+#define CPF_DISPATCH(dtype, CALL)                                   \
+  try {                                                             \
+    if ((dtype) == CPF_F32) { using R = float; return CALL; }       \
+    if ((dtype) == CPF_F64) { using R = double; return CALL; }      \
+    return fail(CPF_ERR_INVALID, "unknown dtype");                  \
+  } catch (const std::exception& e) {                               \
+    return fail(CPF_ERR_NOMEM, e.what());                           \
+  }
+
+int cpf_unitary(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles, void* u_out,
+                void* stream) {
+  if (!prog || !angles || !u_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  if (batch == 0) return CPF_OK;
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  CPF_DISPATCH(dtype, (run_unitary<R>(p, batch, angles, u_out, (cudaStream_t)stream)));
+}
+
+int cpf_loss_grad(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_penalty_spec* penalty,
+                  int32_t dtype, int64_t batch, const void* angles, void* loss_out, void* reg_out,
+                  void* grad_out, void* stream) {
+  if (!prog || !angles || !loss_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  int rc = check_loss(loss);
+  if (rc) return rc;
+  if (batch == 0) return CPF_OK;
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  CPF_DISPATCH(dtype, (run_loss_grad<R>(p, loss, penalty, batch, angles, loss_out, reg_out, grad_out,
+                                        (cudaStream_t)stream)));
+}
+
+int cpf_adjoint_from_cotangent(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles,
+                               const void* cotangent, void* grad_out, void* stream) {
+  if (!prog || !angles || !cotangent || !grad_out || batch < 0)
+    return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  if (batch == 0) return CPF_OK;
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  CPF_DISPATCH(dtype, (run_cotangent<R>(p, batch, angles, cotangent, grad_out, (cudaStream_t)stream)));
+}
+
+int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_penalty_spec* penalty,
+                 const cpf_adam_spec* adam, int32_t dtype, int64_t batch, int64_t step0, int64_t num_steps,
+                 const cpf_adam_buffers* buf, void* stream) {
+  if (!prog || !adam || !buf || batch < 0 || step0 < 0 || num_steps < 0)
+    return fail(CPF_ERR_INVALID, "NULL argument / negative size");
+  int rc = check_loss(loss);
+  if (rc) return rc;
+  if (!buf->angles || !buf->m || !buf->v || !buf->best_params || !buf->best_regloss || !buf->best_reg ||
+      !buf->init_regloss || !buf->init_reg)
+    return fail(CPF_ERR_INVALID, "a required cpf_adam_buffers pointer is NULL");
+  if ((buf->hist_params || buf->hist_regloss) && buf->hist_len <= 0)
+    return fail(CPF_ERR_INVALID, "history buffers given with hist_len <= 0");
+  if (num_steps > 2000000000LL) return fail(CPF_ERR_INVALID, "num_steps too large");
+  if (batch == 0 || num_steps == 0) return CPF_OK;
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  CPF_DISPATCH(dtype, (run_adam<R>(p, loss, penalty, adam, batch, step0, num_steps, buf,
+                                   (cudaStream_t)stream)));
+}
+
+int cpf_count_cz(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles, double threshold,
+                 int32_t* cz_out, void* projected, uint8_t* frozen, void* stream) {
+  if (!prog || !angles || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  if (batch == 0) return CPF_OK;
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  cpf::DeviceProgram d;
+  int rc = device_program(p, &d);
+  if (rc) return rc;
+  dim3 block(32, 8);
+  const unsigned grid = (unsigned)((batch + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CPF_F32)
+    count_cz_kernel<float><<<grid, block, 0, st>>>(d.cp, (int)p->cp.size(), p->n_params, batch,
+                                                   (const float*)angles, (float)threshold, cz_out,
+                                                   (float*)projected, frozen);
+  else if (dtype == CPF_F64)
+    count_cz_kernel<double><<<grid, block, 0, st>>>(d.cp, (int)p->cp.size(), p->n_params, batch,
+                                                    (const double*)angles, threshold, cz_out,
+                                                    (double*)projected, frozen);
+  else
+    return fail(CPF_ERR_INVALID, "unknown dtype");
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+int cpf_initial_angles(const cpf_program* prog, int32_t dtype, uint64_t seed, int64_t total_samples,
+                       int64_t first, int64_t count, int32_t cp_dist, void* out, void* stream) {
+  if (!prog || !out || total_samples < 0 || first < 0 || count < 0 || first + count > total_samples)
+    return fail(CPF_ERR_INVALID, "bad sample range");
+  if (cp_dist != 0 && cp_dist != 1) return fail(CPF_ERR_UNSUPPORTED, "cp_dist must be 0 ('uniform') or 1 ('0')");
+  if (2 * (total_samples + 1) > 0xffffffffLL) return fail(CPF_ERR_UNSUPPORTED, "too many samples for a 32-bit counter");
+  if (count == 0) return CPF_OK;
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  cpf::DeviceProgram d;
+  int rc = device_program(p, &d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t hi = (uint32_t)(seed >> 32), lo = (uint32_t)(seed & 0xffffffffu);
+  if (dtype == CPF_F32)
+    initial_angles_kernel<float><<<(unsigned)count, 128, 0, st>>>(d.cp, (int)p->cp.size(), p->n_params, hi, lo,
+                                                                total_samples, first, count, cp_dist, (float*)out);
+  else if (dtype == CPF_F64)
+    initial_angles_kernel<double><<<(unsigned)count, 128, 0, st>>>(d.cp, (int)p->cp.size(), p->n_params, hi, lo,
+                                                                 total_samples, first, count, cp_dist, (double*)out);
+  else
+    return fail(CPF_ERR_INVALID, "unknown dtype");
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+int cpf_eval_cost(const cpf_program* prog, int32_t loss_kind, int32_t dtype, double* flops, double* bytes) {
+  if (!prog) return fail(CPF_ERR_INVALID, "NULL program");
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  const double N = (double)(1 << p->n_qubits);
+  const double C = loss_kind == CPF_LOSS_STATE ? 1.0 : N;
+  const double rs = dtype == CPF_F64 ? 8.0 : 4.0;
+  if (flops) *flops = C * N * (16.0 * p->n_rot + 4.0 * p->n_phase + 8.0);
+  if (bytes) *bytes = 6.0 * p->n_params * rs + 2.0 * rs;
+  return CPF_OK;
+}
+
+}  // extern "C"

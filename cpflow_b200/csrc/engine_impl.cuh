@@ -1,0 +1,423 @@
+// Kernel body of the cpflow_b200 engine (see engine.cuh for the design notes).
+#pragma once
+#include "engine.cuh"
+
+namespace cpf {
+
+// ---- TMA (bulk async copy) + mbarrier helpers: stage the packed target into shared memory ---
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <typename R> struct Vec4Load;
+template <> struct Vec4Load<float> {
+  static __device__ __forceinline__ void ld(const float* p, float& a, float& b, float& c, float& d) {
+    float4 t = *reinterpret_cast<const float4*>(p); a = t.x; b = t.y; c = t.z; d = t.w;
+  }
+};
+template <> struct Vec4Load<double> {
+  static __device__ __forceinline__ void ld(const double* p, double& a, double& b, double& c, double& d) {
+    double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 2);
+    a = t.x; b = t.y; c = u.x; d = u.y;
+  }
+};
+
+template <typename R>
+__device__ __forceinline__ R sel3(int a, R x, R y, R z) { return a == 0 ? x : (a == 1 ? y : z); }
+
+enum Phase : int { PH_COEF = 0, PH_ADAM = 1, PH_GRAD = 2 };
+
+template <typename R, int NQ, int CPT, bool SINGLE>
+__host__ __device__ constexpr int min_blocks() {
+  if (SINGLE) return 4;
+  if (sizeof(R) == 8) return NQ >= 5 ? 1 : (NQ == 4 ? 3 : 4);
+  return NQ >= 5 ? 2 : (NQ == 4 ? (CPT == 2 ? 2 : 4) : 4);
+}
+
+template <typename R, int NQ, int CPT, bool SINGLE>
+__global__ void __launch_bounds__(Cfg<R, NQ, CPT, SINGLE>::BLOCK, min_blocks<R, NQ, CPT, SINGLE>())
+engine_kernel(const KParams<R> p) {
+  using C = Cfg<R, NQ, CPT, SINGLE>;
+  using CO = Cols<R, NQ, CPT>;
+  using T = VT<R, CPT>;
+  using V = typename T::V;
+  constexpr int N = C::N, TPS = C::TPS, SPB = C::SPB;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  R* s_target = reinterpret_cast<R*>(smem_raw);
+  uint32_t* s_sched = reinterpret_cast<uint32_t*>(smem_raw + p.target_bytes);
+  R* s_coef = reinterpret_cast<R*>(s_sched + ((p.n_sched + 3) & ~3));
+
+  const int tid = threadIdx.x;
+  const bool need_target = p.mode == M_ADAM || p.mode == M_LOSSGRAD;
+
+  // ---- prologue: TMA-stage the target, copy the schedule ----
+  if (need_target) {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&s_bar, (uint32_t)p.target_bytes);
+      tma_bulk_g2s(s_target, p.target_packed, (uint32_t)p.target_bytes, &s_bar);
+    }
+  }
+  for (int i = tid; i < p.n_sched; i += C::BLOCK) s_sched[i] = p.sched[i];
+  __syncthreads();
+  if (need_target) mbar_wait(&s_bar, 0);
+
+  const int sl = tid / TPS;   // sample within the block
+  const int ls = tid % TPS;   // lane within the sample
+  const long long b_raw = (long long)blockIdx.x * SPB + sl;
+  const bool active = b_raw < p.B;
+  const long long b = active ? b_raw : p.B - 1;
+  const int col0 = ls * CPT;
+  const int P = p.P;
+  R* coef = s_coef + (size_t)sl * p.coef_stride;
+  R* coef_cp = coef + 8 * p.n_su2;
+  const V* tv = reinterpret_cast<const V*>(s_target) + 2 * (SINGLE ? 0 : ls * (N + 1));
+
+  R* ang = p.angles + b * P;   // M_LOSSGRAD/UNITARY/COTANGENT: read-only use
+  R* mom = p.m ? p.m + b * P : nullptr;
+  R* vel = p.v ? p.v + b * P : nullptr;
+  const uint8_t* frz = p.freeze ? p.freeze + b * P : nullptr;
+  const R NN = SINGLE ? R(1) : R(N) * R(N);
+
+  R best = R(0), best_reg_v = R(0);
+  if (p.mode == M_ADAM && p.step0 > 0) { best = p.best_regloss[b]; best_reg_v = p.best_reg[b]; }
+
+  // ------------------------------------------------------------------------------------
+  // parameter phase (threads of a sample split the gates between them)
+  // ------------------------------------------------------------------------------------
+  auto param_phase = [&](int phase, long long gi, bool skip_coef) -> R {
+    R reg_part = R(0);
+    R bc1 = R(1), bc2 = R(1);
+    if (phase == PH_ADAM) {
+      const R t = R(gi + 1);
+      bc1 = R(1) - pow_r(p.b1, t);
+      bc2 = R(1) - pow_r(p.b2, t);
+    }
+    auto apply_grad = [&](int pi, R g, R& th) {
+      if (phase == PH_GRAD) {
+        if (active) p.grad_out[b * P + pi] = g;
+        return;
+      }
+      if (frz && frz[pi]) return;
+      R mu = gi == 0 ? R(0) : mom[pi];
+      R nu = gi == 0 ? R(0) : vel[pi];
+      mu = add_rn(mul_rn(p.omb1, g), mul_rn(p.b1, mu));
+      nu = add_rn(mul_rn(p.omb2, mul_rn(g, g)), mul_rn(p.b2, nu));
+      const R mu_hat = mu / bc1, nu_hat = nu / bc2;
+      const R upd = mu_hat / add_rn(sqrt_r(nu_hat), p.eps);
+      th = add_rn(th, mul_rn(-p.lr, upd));
+      if (active) {
+        mom[pi] = mu; vel[pi] = nu; ang[pi] = th;
+        if (p.hist_params && gi + 1 < p.hist_len)
+          p.hist_params[(b * p.hist_len + gi + 1) * P + pi] = th;
+      }
+    };
+
+    for (int g = ls; g < p.n_su2; g += TPS) {
+      const Su2Meta* md = p.su2 + g;
+      R* cf = coef + 8 * g;
+      int ax[3], pi[3];
+      R th[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        ax[k] = md->axis[k];
+        pi[k] = md->pidx[k];
+        th[k] = pi[k] >= 0 ? ang[pi[k]] : R(md->cangle[k]);
+      }
+      if (phase != PH_COEF) {
+        const R sx = cf[0], sy = cf[1], sz = cf[2];
+        const R c2 = cf[4], s2 = cf[5], c3 = cf[6], s3 = cf[7];
+        const R C2 = c2 * c2 - s2 * s2, S2 = R(2) * c2 * s2;
+        const R C3 = c3 * c3 - s3 * s3, S3 = R(2) * c3 * s3;
+        if (pi[2] >= 0) apply_grad(pi[2], sel3(ax[2], sx, sy, sz), th[2]);
+        if (pi[1] >= 0) {
+          R x = ax[1] == 0, y = ax[1] == 1, z = ax[1] == 2;
+          rot_axis(ax[2], C3, S3, x, y, z);
+          apply_grad(pi[1], x * sx + y * sy + z * sz, th[1]);
+        }
+        if (pi[0] >= 0) {
+          R x = ax[0] == 0, y = ax[0] == 1, z = ax[0] == 2;
+          rot_axis(ax[1], C2, S2, x, y, z);
+          rot_axis(ax[2], C3, S3, x, y, z);
+          apply_grad(pi[0], x * sx + y * sy + z * sz, th[0]);
+        }
+      }
+      if (!skip_coef) {
+        R c[3], s[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          c[k] = R(1); s[k] = R(0);
+          if (ax[k] >= 0) sincos_r(th[k] * R(0.5), s[k], c[k]);
+        }
+        R ar, ai, br, bi;
+        su2_of(ax[0], c[0], s[0], ar, ai, br, bi);
+#pragma unroll
+        for (int k = 1; k < 3; ++k) {
+          R a2r, a2i, b2r, b2i;
+          su2_of(ax[k], c[k], s[k], a2r, a2i, b2r, b2i);
+          // alpha = a2 a - conj(b2) b ; beta = b2 a + conj(a2) b
+          const R nar = a2r * ar - a2i * ai - (b2r * br + b2i * bi);
+          const R nai = a2r * ai + a2i * ar - (b2r * bi - b2i * br);
+          const R nbr = b2r * ar - b2i * ai + (a2r * br + a2i * bi);
+          const R nbi = b2r * ai + b2i * ar + (a2r * bi - a2i * br);
+          ar = nar; ai = nai; br = nbr; bi = nbi;
+        }
+        cf[0] = ar; cf[1] = ai; cf[2] = br; cf[3] = bi;
+        cf[4] = c[1]; cf[5] = s[1]; cf[6] = c[2]; cf[7] = s[2];
+      }
+    }
+    for (int k = ls; k < p.n_cp; k += TPS) {
+      const CpMeta* md = p.cp + k;
+      R* cf = coef_cp + 2 * k;
+      const int pi = md->pidx;
+      const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
+                          (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
+      R th = pi >= 0 ? ang[pi] : R(md->cangle);
+      if (phase != PH_COEF && pi >= 0) {
+        R g = R(-2) * cf[0];
+        if (pen_on) {
+          R val, slope;
+          penalty_eval(p.pen, th, val, slope);
+          g = add_rn(g, mul_rn(p.pen.r, slope));
+        }
+        apply_grad(pi, g, th);
+      }
+      if (!skip_coef) {
+        R s, c;
+        sincos_r(th, s, c);
+        cf[0] = c; cf[1] = s;
+        if (pen_on) {
+          R val, slope;
+          penalty_eval(p.pen, th, val, slope);
+          reg_part += val;
+        }
+      }
+    }
+    return reg_part;
+  };
+
+  R reg_part = param_phase(PH_COEF, p.step0, false);
+  __syncwarp();
+
+  for (int it = 0; it < p.nsteps; ++it) {
+    const long long gi = p.step0 + it;
+    V pr[N], pi[N];
+    // ---------------- forward sweep: U e_col ----------------
+#pragma unroll
+    for (int j = 0; j < N; ++j) { pr[j] = T::onehot(j, col0); pi[j] = T::bc(R(0)); }
+    for (int i = 0; i < p.n_sched; ++i) {
+      const uint32_t op = s_sched[i];
+      const int kind = op & 15, q0 = (op >> 4) & 15, q1 = (op >> 8) & 15, slot = op >> 16;
+      if (kind == S_SU2) {
+        R ar, ai, br, bi;
+        Vec4Load<R>::ld(coef + 8 * slot, ar, ai, br, bi);
+        CPF_Q_SWITCH(NQ, q0, (CO::template su2<Q>(pr, pi, ar, ai, br, bi)));
+      } else if (kind == S_CP) {
+        const R c = coef_cp[2 * slot], s = coef_cp[2 * slot + 1];
+        CPF_PAIR_SWITCH(NQ, q1, (CO::template phase<QA, QB>(pr, pi, c, s)));
+      } else if (kind == S_CZ) {
+        CPF_PAIR_SWITCH(NQ, q1, (CO::template negate<QA, QB>(pr, pi)));
+      } else {
+        CPF_QQ_SWITCH(NQ, q0, q1, (CO::template cnot<QC, QT>(pr, pi)));
+      }
+    }
+
+    if (p.mode == M_UNITARY) {
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            R* dst = p.u_out + ((b * N + j) * N + col0 + k) * 2;
+            dst[0] = T::get(pr[j], k); dst[1] = T::get(pi[j], k);
+          }
+      }
+      return;
+    }
+
+    // ---------------- loss and adjoint seed ----------------
+    V lr[N], li[N];
+    R loss = R(0), reg = R(0);
+    if (p.mode == M_COTANGENT) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const R* src = p.cot + ((b * N + j) * N + col0) * 2;
+        lr[j] = T::make(src[0], CPT > 1 ? src[2] : R(0));
+        li[j] = T::make(src[1], CPT > 1 ? src[3] : R(0));
+      }
+    } else if (p.loss_kind == CPF_LOSS_RELPHASE) {
+      V acc = T::bc(R(0));
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const V vr = tv[2 * j], vi = tv[2 * j + 1];
+        const V w = T::fma(vi, vi, T::mul(vr, vr));
+        const V q = T::fma(pi[j], pi[j], T::mul(pr[j], pr[j]));
+        acc = T::fma(w, q, acc);
+        const V ws = T::mul(w, T::bc(R(-1) / R(N)));
+        lr[j] = T::mul(ws, pr[j]); li[j] = T::mul(ws, pi[j]);
+      }
+      R a = sample_sum<TPS>(T::hsum(acc));
+      reg = sample_sum<TPS>(reg_part);
+      loss = R(1) - a / R(N);
+    } else {
+      V trp = T::bc(R(0)), tip = trp, tin = trp;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const V vr = tv[2 * j], vi = tv[2 * j + 1];
+        trp = T::fma(vr, pr[j], trp); trp = T::fma(vi, pi[j], trp);
+        tip = T::fma(vr, pi[j], tip); tin = T::fma(vi, pr[j], tin);
+      }
+      const R tr = sample_sum<TPS>(T::hsum(trp));
+      const R ti = sample_sum<TPS>(T::hsum(tip) - T::hsum(tin));
+      reg = sample_sum<TPS>(reg_part);
+      const R ab = sqrt_r(tr * tr + ti * ti);
+      loss = R(1) - mul_rn(ab, ab) / NN;
+      const V a = T::bc(-tr / NN), bq = T::bc(ti / NN), nb = T::bc(-ti / NN);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const V vr = tv[2 * j], vi = tv[2 * j + 1];
+        lr[j] = T::fma(bq, vi, T::mul(a, vr));
+        li[j] = T::fma(nb, vr, T::mul(a, vi));
+      }
+    }
+    reg = mul_rn(p.pen.r, reg);
+
+    if (p.mode == M_LOSSGRAD) {
+      if (active && ls == 0) {
+        p.loss_out[b] = loss;
+        if (p.reg_out) p.reg_out[b] = reg;
+      }
+      if (!p.grad_out) return;
+    } else if (p.mode == M_ADAM) {
+      const R regloss = add_rn(loss, reg);
+      bool improved;
+      if (gi == 0) {
+        improved = true;
+        if (active && ls == 0) { p.init_regloss[b] = regloss; p.init_reg[b] = reg; }
+      } else {
+        improved = regloss < best;
+      }
+      if (improved) {
+        best = regloss; best_reg_v = reg;
+        if (active)
+          for (int i = ls; i < P; i += TPS) p.best_params[b * P + i] = ang[i];
+      }
+      if (active && p.hist_regloss && ls == 0 && gi < p.hist_len)
+        p.hist_regloss[b * p.hist_len + gi] = regloss;
+      if (active && p.hist_params && gi == 0)
+        for (int i = ls; i < P; i += TPS) p.hist_params[b * p.hist_len * P + i] = ang[i];
+    }
+
+    // ---------------- adjoint sweep ----------------
+    for (int i = p.n_sched - 1; i >= 0; --i) {
+      const uint32_t op = s_sched[i];
+      const int kind = op & 15, q0 = (op >> 4) & 15, q1 = (op >> 8) & 15, slot = op >> 16;
+      const bool has_param = (op >> 12) & FLAG_HAS_PARAM;
+      if (kind == S_SU2) {
+        R* cf = coef + 8 * slot;
+        R ar, ai, br, bi;
+        Vec4Load<R>::ld(cf, ar, ai, br, bi);
+        if (has_param) {
+          R sx, sy, sz;
+          CPF_Q_SWITCH(NQ, q0, (CO::template pauli_sums<Q>(pr, pi, lr, li, sx, sy, sz)));
+          sx = sample_sum<TPS>(sx); sy = sample_sum<TPS>(sy); sz = sample_sum<TPS>(sz);
+          __syncwarp();
+          if (ls == 0) { cf[0] = sx; cf[1] = sy; cf[2] = sz; }
+        }
+        CPF_Q_SWITCH(NQ, q0, {
+          CO::template su2<Q>(pr, pi, ar, -ai, -br, -bi);
+          CO::template su2<Q>(lr, li, ar, -ai, -br, -bi);
+        });
+      } else if (kind == S_CP) {
+        R* cf = coef_cp + 2 * slot;
+        const R c = cf[0], s = cf[1];
+        if (has_param) {
+          R s11;
+          CPF_PAIR_SWITCH(NQ, q1, (s11 = CO::template phase_sum<QA, QB>(pr, pi, lr, li)));
+          s11 = sample_sum<TPS>(s11);
+          __syncwarp();
+          if (ls == 0) cf[0] = s11;
+        }
+        CPF_PAIR_SWITCH(NQ, q1, {
+          CO::template phase<QA, QB>(pr, pi, c, -s);
+          CO::template phase<QA, QB>(lr, li, c, -s);
+        });
+      } else if (kind == S_CZ) {
+        CPF_PAIR_SWITCH(NQ, q1, {
+          CO::template negate<QA, QB>(pr, pi);
+          CO::template negate<QA, QB>(lr, li);
+        });
+      } else {
+        CPF_QQ_SWITCH(NQ, q0, q1, {
+          CO::template cnot<QC, QT>(pr, pi);
+          CO::template cnot<QC, QT>(lr, li);
+        });
+      }
+    }
+    __syncwarp();
+    reg_part = param_phase(p.mode == M_ADAM ? PH_ADAM : PH_GRAD, gi, it == p.nsteps - 1);
+    __syncwarp();
+  }
+
+  if (p.mode == M_ADAM && active && ls == 0) {
+    p.best_regloss[b] = best;
+    p.best_reg[b] = best_reg_v;
+  }
+}
+
+// ---- target packing: row-major complex target -> kernel layout (padded rows) ----------------
+// dst index: ((cg * (N + 1) + j) * 2 + part) * CPT + k  with column = cg * CPT + k
+template <typename R>
+__global__ void pack_target_kernel(const R* __restrict__ src, R* __restrict__ dst, int N, int cpt,
+                                   int single) {
+  const int groups = single ? 1 : N / cpt;
+  const int total = groups * (N + 1) * 2 * cpt;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int k = i % cpt, r = i / cpt;
+    int part = r % 2; r /= 2;
+    int j = r % (N + 1), cg = r / (N + 1);
+    R val = R(0);
+    if (j < N) {
+      if (single) val = src[j * 2 + part];
+      else val = src[(j * N + cg * cpt + k) * 2 + part];
+    }
+    dst[i] = val;
+  }
+}
+
+}  // namespace cpf

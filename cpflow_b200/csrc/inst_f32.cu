@@ -1,0 +1,33 @@
+// float32 / complex64 instantiations of the engine (the reference's default x32 mode).
+#include "launch.cuh"
+
+namespace cpf {
+
+template <>
+int launch_engine<float>(const KParams<float>& p, int n, bool single, cudaStream_t st, std::string& err) {
+  if (single) {
+    switch (n) {
+      case 2: return launch_one<float, 2, 1, true>(p, st, err);
+      case 3: return launch_one<float, 3, 1, true>(p, st, err);
+      case 4: return launch_one<float, 4, 1, true>(p, st, err);
+      case 5: return launch_one<float, 5, 1, true>(p, st, err);
+    }
+  } else {
+    switch (n) {
+      case 2: return launch_one<float, 2, 2, false>(p, st, err);
+      case 3: return launch_one<float, 3, 2, false>(p, st, err);
+      case 4: return launch_one<float, 4, 2, false>(p, st, err);
+      case 5: return launch_one<float, 5, 1, false>(p, st, err);
+    }
+  }
+  err = "unsupported number of qubits";
+  return CPF_ERR_UNSUPPORTED;
+}
+
+template <>
+int launch_pack_target<float>(const float* src, float* dst, int n, int cpt, bool single, cudaStream_t st) {
+  pack_target_kernel<float><<<8, 256, 0, st>>>(src, dst, 1 << n, cpt, single ? 1 : 0);
+  return cudaGetLastError() == cudaSuccess ? CPF_OK : CPF_ERR_CUDA;
+}
+
+}  // namespace cpf

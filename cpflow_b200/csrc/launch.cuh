@@ -1,0 +1,53 @@
+// Host launcher for engine_kernel instantiations.
+#pragma once
+#include <string>
+
+#include "engine_impl.cuh"
+
+namespace cpf {
+
+inline int coef_stride_words(int n_su2, int n_cp) {
+  int w = (coef_words(n_su2, n_cp) + 3) & ~3;
+  if (w == 0) w = 4;
+  if (((w / 4) & 1) == 0) w += 4;  // odd number of 16-byte groups: samples of a warp hit distinct banks
+  return w;
+}
+
+template <typename R>
+inline int target_words(int n, int cpt, bool single) {
+  const int N = 1 << n;
+  return (single ? 1 : N / cpt) * (N + 1) * 2 * cpt;
+}
+
+template <typename R, int NQ, int CPT, bool SINGLE>
+int launch_one(KParams<R> p, cudaStream_t st, std::string& err) {
+  using C = Cfg<R, NQ, CPT, SINGLE>;
+  p.coef_stride = coef_stride_words(p.n_su2, p.n_cp);
+  const size_t smem = (size_t)p.target_bytes + (size_t)((p.n_sched + 3) & ~3) * 4 +
+                      (size_t)C::SPB * p.coef_stride * sizeof(R);
+  if (smem > 227 * 1024) {
+    err = "program too large for the shared-memory coefficient store (" + std::to_string(smem) + " bytes)";
+    return CPF_ERR_UNSUPPORTED;
+  }
+  auto kern = engine_kernel<R, NQ, CPT, SINGLE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
+  const long long grid = (p.B + C::SPB - 1) / C::SPB;
+  if (grid <= 0) return CPF_OK;
+  if (grid > 2147483647LL) { err = "batch too large for one launch"; return CPF_ERR_UNSUPPORTED; }
+  kern<<<(unsigned)grid, C::BLOCK, smem, st>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { err = std::string("kernel launch: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
+  return CPF_OK;
+}
+
+// columns per thread chosen for each (dtype, n)
+template <typename R> constexpr int cpt_for(int n) { return 1; }
+template <> constexpr int cpt_for<float>(int n) { return n <= 4 ? 2 : 1; }
+
+template <typename R> int launch_engine(const KParams<R>& p, int n_qubits, bool single,
+                                        cudaStream_t st, std::string& err);
+template <typename R> int launch_pack_target(const R* src, R* dst, int n_qubits, int cpt, bool single,
+                                             cudaStream_t st);
+
+}  // namespace cpf
