@@ -12,14 +12,18 @@
 //   update phase    : gradients from the Pauli sums, penalty slope, optax Adam
 //                     (optimization.py:14-25), then the next parameter phase.
 //
-// Data layout.  A thread owns CPT whole columns of the 2^n x 2^n unitary in registers
-// (amplitude index = compile-time register index, so every single-qubit gate is a register-
-// local butterfly on mask 1<<(n-1-q) and a CP gate is a phase FMA on a register subset — no
-// shuffles on the gate path).  With CPT = 2 the two columns are packed in float2 registers and
-// all gate arithmetic issues as packed FFMA2/FMUL2 (fma.rn.f32x2, sm_100+): the FP32 pipe
-// saturates at half the issue slots, which leaves room for the LDS/SHFL/integer traffic.
-// The TPS = 2^n / CPT threads of a sample sit in one warp; cross-column sums (the loss trace,
-// the per-gate Pauli sums) are xor-butterflies over those lanes.
+// Data layout.  The n amplitude-index bits of a column are split into RB "register bits" (the
+// low bits: 2^RB amplitudes of a column live in one thread's registers at compile-time indices)
+// and LB = n - RB "lane bits" (the high bits select one of 2^LB lanes).  A gate on a register bit
+// is a register-local butterfly (one unrolled code block per register bit); a gate on a lane bit
+// exchanges the partner amplitudes with __shfl_xor_sync on a RUNTIME lane mask, so one code block
+// serves every lane-bit qubit.  Keeping RB small keeps the unrolled code inside the SM's
+// instruction cache: the first version of this kernel held whole columns in registers (RB = n)
+// and ncu showed 58% of all stall cycles were instruction-fetch misses (profiles/r1_v0_*).
+// With CPT = 2 two columns are packed in float2 registers and the gate arithmetic issues as packed
+// FFMA2/FMUL2 (fma.rn.f32x2, sm_100+): the FP32 pipe saturates at half the issue slots, which
+// leaves room for the SHFL/LDS/integer traffic.  The TPS = (2^n / CPT) * 2^LB threads of a sample
+// sit in one warp; cross-column sums (loss trace, per-gate Pauli sums) are xor-butterflies.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -101,8 +105,11 @@ static __device__ __noinline__ void sincos_slow_f(float x, float* s, float* c) {
 
 // sin/cos with Cody-Waite reduction and the Cephes single-precision kernels (~1 ulp), no
 // local-memory slow path inlined.  XLA-class accuracy is required for 1e-5 parity.
-__device__ __forceinline__ void sincos_r(float x, float& s, float& c) {
-  if (fabsf(x) > 48000.f) { sincos_slow_f(x, &s, &c); return; }
+template <typename R> struct SinCos { R s, c; };
+
+static __device__ __noinline__ SinCos<float> sincos_nr(float x) {
+  float s, c;
+  if (fabsf(x) > 48000.f) { sincos_slow_f(x, &s, &c); return {s, c}; }
   float j = rintf(x * 0.636619747f);
   float r = fmaf(j, -1.57079601e+00f, x);
   r = fmaf(j, -3.13916473e-07f, r);
@@ -119,8 +126,17 @@ __device__ __forceinline__ void sincos_r(float x, float& s, float& c) {
   float cc = (q & 1) ? sp : cp;
   s = (q & 2) ? -ss : ss;
   c = ((q + 1) & 2) ? -cc : cc;
+  return {s, c};
 }
-__device__ __forceinline__ void sincos_r(double x, double& s, double& c) { sincos(x, &s, &c); }
+static __device__ __noinline__ SinCos<double> sincos_nr(double x) {
+  double s, c;
+  sincos(x, &s, &c);
+  return {s, c};
+}
+// out-of-line on purpose: the parameter phase must stay small so that the whole hot loop fits
+// in the SM instruction cache.
+__device__ __forceinline__ void sincos_r(float x, float& s, float& c) { auto r = sincos_nr(x); s = r.s; c = r.c; }
+__device__ __forceinline__ void sincos_r(double x, double& s, double& c) { auto r = sincos_nr(x); s = r.s; c = r.c; }
 
 // IEEE operations that must NOT be contracted into FMAs (optax/XLA evaluate the Adam update and
 // the penalty line as separate multiplies and adds; the oracle does the same).
@@ -130,8 +146,9 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float sqrt_r(float a) { return sqrtf(a); }
 __device__ __forceinline__ double sqrt_r(double a) { return sqrt(a); }
-__device__ __forceinline__ float pow_r(float a, float b) { return powf(a, b); }
-__device__ __forceinline__ double pow_r(double a, double b) { return pow(a, b); }
+// 1 - b^t (optax bias correction); float: exp2(t*log2 b), ~1e-7 relative like an f32 pow
+static __device__ __noinline__ float bias_corr(float b, float t) { return 1.0f - exp2f(t * log2f(b)); }
+static __device__ __noinline__ double bias_corr(double b, double t) { return 1.0 - pow(b, t); }
 __device__ __forceinline__ float fmod_r(float a, float b) { return fmodf(a, b); }
 __device__ __forceinline__ double fmod_r(double a, double b) { return fmod(a, b); }
 __device__ __forceinline__ float abs_r(float a) { return fabsf(a); }
@@ -149,7 +166,7 @@ __device__ __forceinline__ R sample_sum(R x) {
 
 // jnp.mod semantics (result has the sign of the divisor; period > 0)
 template <typename R>
-__device__ __forceinline__ R pymod(R a, R period) {
+static __device__ __noinline__ R pymod(R a, R period) {
   R r = fmod_r(a, period);
   if (r != R(0) && r < R(0)) r = add_rn(r, period);
   return r;
@@ -161,6 +178,7 @@ __device__ __forceinline__ void penalty_eval(const PenaltyT<R>& pen, R a, R& val
   val = R(0); slope = R(0);
   if (pen.kind == CPF_PEN_PIECEWISE) {
     R am = pymod(a, pen.period);
+#pragma unroll 1
     for (int s = 0; s < pen.nseg; ++s) {
       if (pen.lo[s] < am && am <= pen.hi[s]) {
         val = add_rn(mul_rn(pen.slope[s], am), pen.icpt[s]);
@@ -172,6 +190,19 @@ __device__ __forceinline__ void penalty_eval(const PenaltyT<R>& pen, R a, R& val
     val = abs_r(a);
     slope = a > R(0) ? R(1) : (a < R(0) ? R(-1) : R(0));
   }
+}
+
+// optax 0.1.1 scale_by_adam + scale(-lr), one parameter (optimization.py:22-23); out of line
+template <typename R> struct AdamOut { R th, mu, nu; };
+template <typename R>
+static __device__ __noinline__ AdamOut<R> adam_step(R g, R th, R mu, R nu, R b1, R omb1, R b2, R omb2,
+                                                    R bc1, R bc2, R eps, R neg_lr) {
+  mu = add_rn(mul_rn(omb1, g), mul_rn(b1, mu));
+  nu = add_rn(mul_rn(omb2, mul_rn(g, g)), mul_rn(b2, nu));
+  const R mu_hat = mu / bc1, nu_hat = nu / bc2;
+  const R upd = mu_hat / add_rn(sqrt_r(nu_hat), eps);
+  th = add_rn(th, mul_rn(neg_lr, upd));
+  return {th, mu, nu};
 }
 
 // rotate vector (x,y,z) by angle with cos C, sin S about coordinate axis `a` (right-handed):
@@ -193,23 +224,46 @@ __device__ __forceinline__ void su2_of(int a, R c, R s, R& ar, R& ai, R& br, R& 
   else if (a == 2) ai = -s;   // Rz: alpha = c - i s
 }
 
+// (alpha, beta) <- (a2, b2) * (alpha, beta):  alpha = a2 a - conj(b2) b ; beta = b2 a + conj(a2) b
+template <typename R>
+__device__ __forceinline__ void su2_mul(R a2r, R a2i, R b2r, R b2i, R& ar, R& ai, R& br, R& bi) {
+  const R nar = a2r * ar - a2i * ai - (b2r * br + b2i * bi);
+  const R nai = a2r * ai + a2i * ar - (b2r * bi - b2i * br);
+  const R nbr = b2r * ar - b2i * ai + (a2r * br + a2i * bi);
+  const R nbi = b2r * ai + b2i * ar + (a2r * bi - a2i * br);
+  ar = nar; ai = nai; br = nbr; bi = nbi;
+}
+
 // ------------------------------------------------------------------------------------------
-// gate application on register-resident columns
+// gate application on the register/lane-split columns
 // ------------------------------------------------------------------------------------------
-template <typename R, int NQ, int CPT>
+template <typename V> struct ShflV;
+template <> struct ShflV<float> {
+  static __device__ __forceinline__ float x(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+};
+template <> struct ShflV<double> {
+  static __device__ __forceinline__ double x(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+};
+template <> struct ShflV<float2> {
+  static __device__ __forceinline__ float2 x(float2 v, int m) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+  }
+};
+
+template <typename R, int RB, int CPT>
 struct Cols {
   using T = VT<R, CPT>;
   using V = typename T::V;
-  static constexpr int N = 1 << NQ;
+  static constexpr int NA = 1 << RB;  // amplitudes of a column held by one thread
 
-  // x' = alpha x - conj(beta) y ; y' = beta x + conj(alpha) y on qubit Q (big-endian mask)
-  template <int Q>
-  static __device__ __forceinline__ void su2(V (&re)[N], V (&im)[N], R ar, R ai, R br, R bi) {
-    constexpr int M = 1 << (NQ - 1 - Q);
+  // ---- register-bit butterfly: x' = alpha x - conj(beta) y ; y' = beta x + conj(alpha) y ----
+  template <int BP>
+  static __device__ __forceinline__ void su2_reg(V (&re)[NA], V (&im)[NA], R ar, R ai, R br, R bi) {
+    constexpr int M = 1 << BP;
     const V Ar = T::bc(ar), Ai = T::bc(ai), nAi = T::bc(-ai);
     const V Br = T::bc(br), nBr = T::bc(-br), Bi = T::bc(bi), nBi = T::bc(-bi);
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
+    for (int j = 0; j < NA; ++j) {
       if (j & M) continue;
       const V xr = re[j], xi = im[j], yr = re[j | M], yi = im[j | M];
       re[j] = T::fma(nBi, yi, T::fma(nBr, yr, T::fma(nAi, xi, T::mul(Ar, xr))));
@@ -219,16 +273,15 @@ struct Cols {
     }
   }
 
-  // Pauli sums S_a = Im <lam| sigma_a |phi> on qubit Q, split in positive / negative parts so
-  // that every term is a plain FMA (no operand negation on the packed path).
-  template <int Q>
-  static __device__ __forceinline__ void pauli_sums(const V (&pr)[N], const V (&pi)[N],
-                                                    const V (&lr)[N], const V (&li)[N],
-                                                    R& sx, R& sy, R& sz) {
-    constexpr int M = 1 << (NQ - 1 - Q);
+  // Pauli sums S_a = Im <lam| sigma_a |phi> for a register bit
+  template <int BP>
+  static __device__ __forceinline__ void pauli_reg(const V (&pr)[NA], const V (&pi)[NA],
+                                                   const V (&lr)[NA], const V (&li)[NA],
+                                                   R& sx, R& sy, R& sz) {
+    constexpr int M = 1 << BP;
     V xp = T::bc(R(0)), xn = xp, yp = xp, yn = xp, zp = xp, zn = xp;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
+    for (int j = 0; j < NA; ++j) {
       if (j & M) continue;
       const int k = j | M;
       zp = T::fma(lr[j], pi[j], zp); zn = T::fma(li[j], pr[j], zn);
@@ -243,105 +296,151 @@ struct Cols {
     sz = T::hsum(zp) - T::hsum(zn);
   }
 
-  // multiply amplitudes with both bits set by (c + i s)
-  template <int QA, int QB>
-  static __device__ __forceinline__ void phase(V (&re)[N], V (&im)[N], R c, R s) {
-    constexpr int M = (1 << (NQ - 1 - QA)) | (1 << (NQ - 1 - QB));
+  // ---- lane-bit butterfly: new = A * mine + B * partner with per-lane (A, B) ----
+  //   my bit 0: A = alpha,       B = -conj(beta)
+  //   my bit 1: A = conj(alpha), B = beta
+  static __device__ __forceinline__ void lane_coef(bool mybit, R ar, R ai, R br, R bi,
+                                                   R& Ar, R& Ai, R& Br, R& Bi) {
+    Ar = ar; Ai = mybit ? -ai : ai;
+    Br = mybit ? br : -br; Bi = bi;
+  }
+  static __device__ __forceinline__ void mix(V (&re)[NA], V (&im)[NA], const V (&qr)[NA],
+                                             const V (&qi)[NA], R Ar, R Ai, R Br, R Bi) {
+    const V vAr = T::bc(Ar), vAi = T::bc(Ai), nAi = T::bc(-Ai);
+    const V vBr = T::bc(Br), vBi = T::bc(Bi), nBi = T::bc(-Bi);
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const V mr = re[j], mi = im[j];
+      re[j] = T::fma(nBi, qi[j], T::fma(vBr, qr[j], T::fma(nAi, mi, T::mul(vAr, mr))));
+      im[j] = T::fma(vBi, qr[j], T::fma(vBr, qi[j], T::fma(vAi, mr, T::mul(vAr, mi))));
+    }
+  }
+  static __device__ __forceinline__ void su2_lane(V (&re)[NA], V (&im)[NA], int lm, bool mybit,
+                                                  R ar, R ai, R br, R bi) {
+    V qr[NA], qi[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) { qr[j] = ShflV<V>::x(re[j], lm); qi[j] = ShflV<V>::x(im[j], lm); }
+    R Ar, Ai, Br, Bi;
+    lane_coef(mybit, ar, ai, br, bi, Ar, Ai, Br, Bi);
+    mix(re, im, qr, qi, Ar, Ai, Br, Bi);
+  }
+  // adjoint step on a lane bit: Pauli sums (this lane's share) then the inverse butterfly on both
+  // phi and lambda, sharing the partner exchange.
+  static __device__ __forceinline__ void bwd_lane(V (&pr)[NA], V (&pi)[NA], V (&lr)[NA], V (&li)[NA],
+                                                  int lm, bool mybit, bool want_sums, R ar, R ai,
+                                                  R br, R bi, R& sx, R& sy, R& sz) {
+    V qr[NA], qi[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) { qr[j] = ShflV<V>::x(pr[j], lm); qi[j] = ShflV<V>::x(pi[j], lm); }
+    if (want_sums) {
+      V xp = T::bc(R(0)), xn = xp, yp = xp, zp = xp, zn = xp;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        zp = T::fma(lr[j], pi[j], zp); zn = T::fma(li[j], pr[j], zn);   // Im(conj(l) p), own
+        xp = T::fma(lr[j], qi[j], xp); xn = T::fma(li[j], qr[j], xn);   // Im(conj(l) partner)
+        yp = T::fma(lr[j], qr[j], yp); yp = T::fma(li[j], qi[j], yp);   // Re(conj(l) partner)
+      }
+      const R z = T::hsum(zp) - T::hsum(zn), y = T::hsum(yp);
+      sx = T::hsum(xp) - T::hsum(xn);
+      sz = mybit ? -z : z;
+      sy = mybit ? y : -y;
+    }
+    R Ar, Ai, Br, Bi;
+    lane_coef(mybit, ar, -ai, -br, -bi, Ar, Ai, Br, Bi);   // inverse gate
+    mix(pr, pi, qr, qi, Ar, Ai, Br, Bi);
+#pragma unroll
+    for (int j = 0; j < NA; ++j) { qr[j] = ShflV<V>::x(lr[j], lm); qi[j] = ShflV<V>::x(li[j], lm); }
+    mix(lr, li, qr, qi, Ar, Ai, Br, Bi);
+  }
+
+  // ---- diagonal two-qubit phases: multiply amplitudes whose register bits RM are all set ----
+  // (the lane-bit part of the |11> condition is folded into (c, s) by the caller: lanes that do not
+  // satisfy it pass (1, 0))
+  template <int RM>
+  static __device__ __forceinline__ void phase(V (&re)[NA], V (&im)[NA], R c, R s) {
     const V C = T::bc(c), S = T::bc(s), nS = T::bc(-s);
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      if ((j & M) != M) continue;
+    for (int j = 0; j < NA; ++j) {
+      if ((j & RM) != RM) continue;
       const V xr = re[j], xi = im[j];
       re[j] = T::fma(nS, xi, T::mul(C, xr));
       im[j] = T::fma(S, xr, T::mul(C, xi));
     }
   }
-  template <int QA, int QB>
-  static __device__ __forceinline__ void negate(V (&re)[N], V (&im)[N]) {
-    constexpr int M = (1 << (NQ - 1 - QA)) | (1 << (NQ - 1 - QB));
-    const V m1 = T::bc(R(-1));
+  // ---- CNOT on amplitude-index bit positions (cpos controls, tpos is flipped); `la` is this
+  // thread's lane part of the amplitude index.  Used by 'cx' templates only. ----
+  static __device__ __forceinline__ V selv(bool p, V a, V b) { return p ? a : b; }
+  template <int BP>
+  static __device__ __forceinline__ void cnot_reg(V (&re)[NA], V (&im)[NA], int cpos, int la) {
+    constexpr int M = 1 << BP;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      if ((j & M) != M) continue;
-      re[j] = T::mul(m1, re[j]); im[j] = T::mul(m1, im[j]);
+    for (int j = 0; j < NA; ++j) {
+      if (j & M) continue;
+      const bool c = ((((la << RB) | j) >> cpos) & 1) != 0;
+      const V a = re[j], b = re[j | M], ai = im[j], bi = im[j | M];
+      re[j] = selv(c, b, a); re[j | M] = selv(c, a, b);
+      im[j] = selv(c, bi, ai); im[j | M] = selv(c, ai, bi);
     }
   }
-  // sum over |11> amplitudes of Im(conj(lam) phi)
-  template <int QA, int QB>
-  static __device__ __forceinline__ R phase_sum(const V (&pr)[N], const V (&pi)[N],
-                                                const V (&lr)[N], const V (&li)[N]) {
-    constexpr int M = (1 << (NQ - 1 - QA)) | (1 << (NQ - 1 - QB));
+  static __device__ __forceinline__ void cnot_lane(V (&re)[NA], V (&im)[NA], int cpos, int lm, int la) {
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const bool c = ((((la << RB) | j) >> cpos) & 1) != 0;
+      const V qr = ShflV<V>::x(re[j], lm), qi = ShflV<V>::x(im[j], lm);
+      re[j] = selv(c, qr, re[j]); im[j] = selv(c, qi, im[j]);
+    }
+  }
+  template <int RM>
+  static __device__ __forceinline__ R phase_sum(const V (&pr)[NA], const V (&pi)[NA],
+                                                const V (&lr)[NA], const V (&li)[NA]) {
     V p = T::bc(R(0)), n = p;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      if ((j & M) != M) continue;
+    for (int j = 0; j < NA; ++j) {
+      if ((j & RM) != RM) continue;
       p = T::fma(lr[j], pi[j], p); n = T::fma(li[j], pr[j], n);
     }
     return T::hsum(p) - T::hsum(n);
   }
-  // CNOT: swap target bit where control bit is set (register renaming, no arithmetic)
-  template <int QC, int QT>
-  static __device__ __forceinline__ void cnot(V (&re)[N], V (&im)[N]) {
-    constexpr int MC = 1 << (NQ - 1 - QC), MT = 1 << (NQ - 1 - QT);
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      if (!(j & MC) || (j & MT)) continue;
-      V t = re[j]; re[j] = re[j | MT]; re[j | MT] = t;
-      t = im[j]; im[j] = im[j | MT]; im[j | MT] = t;
-    }
-  }
 };
 
-// ---- compile-time qubit dispatch ----------------------------------------------------------
-#define CPF_Q_SWITCH(NQ, q, ...)                                               \
-  switch (q) {                                                                 \
-    case 0: { constexpr int Q = 0; __VA_ARGS__; } break;                              \
-    case 1: { constexpr int Q = 1; __VA_ARGS__; } break;                              \
-    case 2: if constexpr (NQ > 2) { constexpr int Q = 2; __VA_ARGS__; } break;        \
-    case 3: if constexpr (NQ > 3) { constexpr int Q = 3; __VA_ARGS__; } break;        \
-    case 4: if constexpr (NQ > 4) { constexpr int Q = 4; __VA_ARGS__; } break;        \
+// ---- compile-time dispatch over register bit positions / register masks ---------------------
+#define CPF_BP_SWITCH(RB, bp, ...)                                             \
+  switch (bp) {                                                                \
+    case 0: if constexpr (RB > 0) { constexpr int BP = 0; __VA_ARGS__; } break; \
+    case 1: if constexpr (RB > 1) { constexpr int BP = 1; __VA_ARGS__; } break; \
+    case 2: if constexpr (RB > 2) { constexpr int BP = 2; __VA_ARGS__; } break; \
+    case 3: if constexpr (RB > 3) { constexpr int BP = 3; __VA_ARGS__; } break; \
+    case 4: if constexpr (RB > 4) { constexpr int BP = 4; __VA_ARGS__; } break; \
     default: break;                                                            \
   }
-
-// pair index -> (QA < QB), lexicographic, must match cpf::pair_index
-template <int NQ, int IDX> struct PairOf {
-  static __host__ __device__ constexpr int a() { int i = IDX, a = 0; while (i >= NQ - 1 - a) { i -= NQ - 1 - a; ++a; } return a; }
-  static __host__ __device__ constexpr int b() { int i = IDX, a = 0; while (i >= NQ - 1 - a) { i -= NQ - 1 - a; ++a; } return a + 1 + i; }
-};
-#define CPF_PAIR_CASE(NQ, I, ...)                                              \
-  case I: if constexpr (I < NQ * (NQ - 1) / 2) {                               \
-    constexpr int QA = PairOf<NQ, I>::a(); constexpr int QB = PairOf<NQ, I>::b(); __VA_ARGS__; } break;
-#define CPF_PAIR_SWITCH(NQ, p, ...)                                            \
-  switch (p) {                                                                 \
-    CPF_PAIR_CASE(NQ, 0, __VA_ARGS__) CPF_PAIR_CASE(NQ, 1, __VA_ARGS__) CPF_PAIR_CASE(NQ, 2, __VA_ARGS__)  \
-    CPF_PAIR_CASE(NQ, 3, __VA_ARGS__) CPF_PAIR_CASE(NQ, 4, __VA_ARGS__) CPF_PAIR_CASE(NQ, 5, __VA_ARGS__)  \
-    CPF_PAIR_CASE(NQ, 6, __VA_ARGS__) CPF_PAIR_CASE(NQ, 7, __VA_ARGS__) CPF_PAIR_CASE(NQ, 8, __VA_ARGS__)  \
-    CPF_PAIR_CASE(NQ, 9, __VA_ARGS__)                                                 \
+#define CPF_RM_CASE(RB, I, ...)                                                \
+  case I: if constexpr (I < (1 << RB)) { constexpr int RM = I; __VA_ARGS__; } break;
+// RM has at most two bits set (a two-qubit gate)
+#define CPF_RM_SWITCH(RB, rm, ...)                                             \
+  switch (rm) {                                                                \
+    CPF_RM_CASE(RB, 0, __VA_ARGS__) CPF_RM_CASE(RB, 1, __VA_ARGS__) CPF_RM_CASE(RB, 2, __VA_ARGS__)    \
+    CPF_RM_CASE(RB, 3, __VA_ARGS__) CPF_RM_CASE(RB, 4, __VA_ARGS__) CPF_RM_CASE(RB, 5, __VA_ARGS__)    \
+    CPF_RM_CASE(RB, 6, __VA_ARGS__) CPF_RM_CASE(RB, 8, __VA_ARGS__) CPF_RM_CASE(RB, 9, __VA_ARGS__)    \
+    CPF_RM_CASE(RB, 10, __VA_ARGS__) CPF_RM_CASE(RB, 12, __VA_ARGS__) CPF_RM_CASE(RB, 16, __VA_ARGS__) \
+    CPF_RM_CASE(RB, 17, __VA_ARGS__) CPF_RM_CASE(RB, 18, __VA_ARGS__) CPF_RM_CASE(RB, 20, __VA_ARGS__) \
+    CPF_RM_CASE(RB, 24, __VA_ARGS__)                                           \
     default: break;                                                            \
   }
-// ordered (control, target) dispatch for CX
-#define CPF_QQ_SWITCH(NQ, qc, qt, ...)                                         \
-  CPF_Q_SWITCH(NQ, qc, { constexpr int QC = Q; switch (qt) {                   \
-    case 0: if constexpr (QC != 0) { constexpr int QT = 0; __VA_ARGS__; } break;      \
-    case 1: if constexpr (QC != 1) { constexpr int QT = 1; __VA_ARGS__; } break;      \
-    case 2: if constexpr (NQ > 2 && QC != 2) { constexpr int QT = 2; __VA_ARGS__; } break; \
-    case 3: if constexpr (NQ > 3 && QC != 3) { constexpr int QT = 3; __VA_ARGS__; } break; \
-    case 4: if constexpr (NQ > 4 && QC != 4) { constexpr int QT = 4; __VA_ARGS__; } break; \
-    default: break; } })
 
 // ------------------------------------------------------------------------------------------
 // kernel configuration
 // ------------------------------------------------------------------------------------------
-template <typename R, int NQ, int CPT, bool SINGLE>
+template <typename R, int NQ, int RB, int CPT, bool SINGLE>
 struct Cfg {
   static constexpr int N = 1 << NQ;
+  static constexpr int LB = NQ - RB;
+  static constexpr int NA = 1 << RB;
   static constexpr int COLS = SINGLE ? 1 : N;
-  static constexpr int TPS = COLS / CPT;             // threads per sample (<= 32)
-  static constexpr int BLOCK = SINGLE ? 32 : 128;
+  static constexpr int TPS = (COLS / CPT) << LB;     // threads per sample (<= 32)
+  static constexpr int BLOCK = 128;
   static constexpr int SPB = BLOCK / TPS;            // samples per block
+  static_assert(RB >= 0 && RB <= NQ, "bad register/lane split");
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
-  // packed target in shared memory: per (column group, amplitude): V re, V im
-  static constexpr int TARGET_WORDS = (SINGLE ? N : N * N) * 2;
 };
 
 // per-sample coefficient storage (R words): su2 gate g at [8g, 8g+8) =

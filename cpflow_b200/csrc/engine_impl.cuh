@@ -56,21 +56,45 @@ __device__ __forceinline__ R sel3(int a, R x, R y, R z) { return a == 0 ? x : (a
 
 enum Phase : int { PH_COEF = 0, PH_ADAM = 1, PH_GRAD = 2 };
 
-template <typename R, int NQ, int CPT, bool SINGLE>
-__host__ __device__ constexpr int min_blocks() {
-  if (SINGLE) return 4;
-  if (sizeof(R) == 8) return NQ >= 5 ? 1 : (NQ == 4 ? 3 : 4);
-  return NQ >= 5 ? 2 : (NQ == 4 ? (CPT == 2 ? 2 : 4) : 4);
+// Gradient sink of the update phase: either store the gradient (loss_grad / cotangent modes) or run
+// one optax-Adam step on the parameter (skipped for frozen parameters: cp_utils.py:100-108).
+template <typename R>
+__device__ __forceinline__ void apply_grad(const KParams<R>& p, bool active, long long b, int phase,
+                                           long long gi, R bc1, R bc2, R* ang, R* mom, R* vel,
+                                           const uint8_t* frz, int pi, R g, R& th) {
+  const int P = p.P;
+  if (phase == PH_GRAD) {
+    if (active) p.grad_out[b * P + pi] = g;
+    return;
+  }
+  if (frz && frz[pi]) return;
+  const R mu0 = gi == 0 ? R(0) : mom[pi];
+  const R nu0 = gi == 0 ? R(0) : vel[pi];
+  const AdamOut<R> o = adam_step(g, th, mu0, nu0, p.b1, p.omb1, p.b2, p.omb2, bc1, bc2, p.eps, -p.lr);
+  th = o.th;
+  if (active) {
+    mom[pi] = o.mu; vel[pi] = o.nu; ang[pi] = th;
+    if (p.hist_params && gi + 1 < p.hist_len)
+      p.hist_params[(b * p.hist_len + gi + 1) * P + pi] = th;
+  }
 }
 
-template <typename R, int NQ, int CPT, bool SINGLE>
-__global__ void __launch_bounds__(Cfg<R, NQ, CPT, SINGLE>::BLOCK, min_blocks<R, NQ, CPT, SINGLE>())
+// resident CTAs per SM the register allocator is asked to allow for (state registers per thread
+// = 4 * 2^RB * CPT * sizeof(R)/4 for phi and lambda together)
+template <typename R, int RB, int CPT>
+__host__ __device__ constexpr int min_blocks() {
+  constexpr int state = 4 * (1 << RB) * CPT * (int)(sizeof(R) / 4);
+  return state <= 32 ? 5 : (state <= 64 ? 4 : (state <= 128 ? 2 : 1));
+}
+
+template <typename R, int NQ, int RB, int CPT, bool SINGLE>
+__global__ void __launch_bounds__(Cfg<R, NQ, RB, CPT, SINGLE>::BLOCK, min_blocks<R, RB, CPT>())
 engine_kernel(const KParams<R> p) {
-  using C = Cfg<R, NQ, CPT, SINGLE>;
-  using CO = Cols<R, NQ, CPT>;
+  using C = Cfg<R, NQ, RB, CPT, SINGLE>;
+  using CO = Cols<R, RB, CPT>;
   using T = VT<R, CPT>;
   using V = typename T::V;
-  constexpr int N = C::N, TPS = C::TPS, SPB = C::SPB;
+  constexpr int N = C::N, TPS = C::TPS, SPB = C::SPB, LB = C::LB, NA = C::NA;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
@@ -102,11 +126,13 @@ engine_kernel(const KParams<R> p) {
   const long long b_raw = (long long)blockIdx.x * SPB + sl;
   const bool active = b_raw < p.B;
   const long long b = active ? b_raw : p.B - 1;
-  const int col0 = ls * CPT;
+  const int cg = ls >> LB;                 // column group
+  const int la = ls & ((1 << LB) - 1);     // lane part of the amplitude index
+  const int col0 = cg * CPT;
   const int P = p.P;
   R* coef = s_coef + (size_t)sl * p.coef_stride;
   R* coef_cp = coef + 8 * p.n_su2;
-  const V* tv = reinterpret_cast<const V*>(s_target) + 2 * (SINGLE ? 0 : ls * (N + 1));
+  const V* tv = reinterpret_cast<const V*>(s_target) + 2 * ((SINGLE ? 0 : cg * (N + 1)) + (la << RB));
 
   R* ang = p.angles + b * P;   // M_LOSSGRAD/UNITARY/COTANGENT: read-only use
   R* mom = p.m ? p.m + b * P : nullptr;
@@ -117,173 +143,155 @@ engine_kernel(const KParams<R> p) {
   R best = R(0), best_reg_v = R(0);
   if (p.mode == M_ADAM && p.step0 > 0) { best = p.best_regloss[b]; best_reg_v = p.best_reg[b]; }
 
-  // ------------------------------------------------------------------------------------
-  // parameter phase (threads of a sample split the gates between them)
-  // ------------------------------------------------------------------------------------
-  auto param_phase = [&](int phase, long long gi, bool skip_coef) -> R {
-    R reg_part = R(0);
-    R bc1 = R(1), bc2 = R(1);
-    if (phase == PH_ADAM) {
-      const R t = R(gi + 1);
-      bc1 = R(1) - pow_r(p.b1, t);
-      bc2 = R(1) - pow_r(p.b2, t);
-    }
-    auto apply_grad = [&](int pi, R g, R& th) {
-      if (phase == PH_GRAD) {
-        if (active) p.grad_out[b * P + pi] = g;
-        return;
-      }
-      if (frz && frz[pi]) return;
-      R mu = gi == 0 ? R(0) : mom[pi];
-      R nu = gi == 0 ? R(0) : vel[pi];
-      mu = add_rn(mul_rn(p.omb1, g), mul_rn(p.b1, mu));
-      nu = add_rn(mul_rn(p.omb2, mul_rn(g, g)), mul_rn(p.b2, nu));
-      const R mu_hat = mu / bc1, nu_hat = nu / bc2;
-      const R upd = mu_hat / add_rn(sqrt_r(nu_hat), p.eps);
-      th = add_rn(th, mul_rn(-p.lr, upd));
-      if (active) {
-        mom[pi] = mu; vel[pi] = nu; ang[pi] = th;
-        if (p.hist_params && gi + 1 < p.hist_len)
-          p.hist_params[(b * p.hist_len + gi + 1) * P + pi] = th;
-      }
-    };
-
-    for (int g = ls; g < p.n_su2; g += TPS) {
-      const Su2Meta* md = p.su2 + g;
-      R* cf = coef + 8 * g;
-      int ax[3], pi[3];
-      R th[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        ax[k] = md->axis[k];
-        pi[k] = md->pidx[k];
-        th[k] = pi[k] >= 0 ? ang[pi[k]] : R(md->cangle[k]);
-      }
-      if (phase != PH_COEF) {
-        const R sx = cf[0], sy = cf[1], sz = cf[2];
-        const R c2 = cf[4], s2 = cf[5], c3 = cf[6], s3 = cf[7];
-        const R C2 = c2 * c2 - s2 * s2, S2 = R(2) * c2 * s2;
-        const R C3 = c3 * c3 - s3 * s3, S3 = R(2) * c3 * s3;
-        if (pi[2] >= 0) apply_grad(pi[2], sel3(ax[2], sx, sy, sz), th[2]);
-        if (pi[1] >= 0) {
-          R x = ax[1] == 0, y = ax[1] == 1, z = ax[1] == 2;
-          rot_axis(ax[2], C3, S3, x, y, z);
-          apply_grad(pi[1], x * sx + y * sy + z * sz, th[1]);
-        }
-        if (pi[0] >= 0) {
-          R x = ax[0] == 0, y = ax[0] == 1, z = ax[0] == 2;
-          rot_axis(ax[1], C2, S2, x, y, z);
-          rot_axis(ax[2], C3, S3, x, y, z);
-          apply_grad(pi[0], x * sx + y * sy + z * sz, th[0]);
-        }
-      }
-      if (!skip_coef) {
-        R c[3], s[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          c[k] = R(1); s[k] = R(0);
-          if (ax[k] >= 0) sincos_r(th[k] * R(0.5), s[k], c[k]);
-        }
-        R ar, ai, br, bi;
-        su2_of(ax[0], c[0], s[0], ar, ai, br, bi);
-#pragma unroll
-        for (int k = 1; k < 3; ++k) {
-          R a2r, a2i, b2r, b2i;
-          su2_of(ax[k], c[k], s[k], a2r, a2i, b2r, b2i);
-          // alpha = a2 a - conj(b2) b ; beta = b2 a + conj(a2) b
-          const R nar = a2r * ar - a2i * ai - (b2r * br + b2i * bi);
-          const R nai = a2r * ai + a2i * ar - (b2r * bi - b2i * br);
-          const R nbr = b2r * ar - b2i * ai + (a2r * br + a2i * bi);
-          const R nbi = b2r * ai + b2i * ar + (a2r * bi - a2i * br);
-          ar = nar; ai = nai; br = nbr; bi = nbi;
-        }
-        cf[0] = ar; cf[1] = ai; cf[2] = br; cf[3] = bi;
-        cf[4] = c[1]; cf[5] = s[1]; cf[6] = c[2]; cf[7] = s[2];
-      }
-    }
-    for (int k = ls; k < p.n_cp; k += TPS) {
-      const CpMeta* md = p.cp + k;
-      R* cf = coef_cp + 2 * k;
-      const int pi = md->pidx;
-      const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
-                          (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
-      R th = pi >= 0 ? ang[pi] : R(md->cangle);
-      if (phase != PH_COEF && pi >= 0) {
-        R g = R(-2) * cf[0];
-        if (pen_on) {
-          R val, slope;
-          penalty_eval(p.pen, th, val, slope);
-          g = add_rn(g, mul_rn(p.pen.r, slope));
-        }
-        apply_grad(pi, g, th);
-      }
-      if (!skip_coef) {
-        R s, c;
-        sincos_r(th, s, c);
-        cf[0] = c; cf[1] = s;
-        if (pen_on) {
-          R val, slope;
-          penalty_eval(p.pen, th, val, slope);
-          reg_part += val;
-        }
-      }
-    }
-    return reg_part;
-  };
-
-  R reg_part = param_phase(PH_COEF, p.step0, false);
-  __syncwarp();
-
-  for (int it = 0; it < p.nsteps; ++it) {
+  // iteration `it` first finishes step it-1 (gradients from the stored Pauli sums, Adam update),
+  // then evaluates step it; one call site keeps the parameter-phase code in the binary once.
+  for (int it = 0; it <= p.nsteps; ++it) {
     const long long gi = p.step0 + it;
-    V pr[N], pi[N];
+    const int phase = it == 0 ? PH_COEF : (p.mode == M_ADAM ? PH_ADAM : PH_GRAD);
+    // ---------------- parameter phase (a sample's threads split the gates) ----------------
+    R reg_part = R(0);
+    {
+      const long long gu = gi - 1;            // the step being finished
+      const bool skip_coef = it == p.nsteps;
+      R bc1 = R(1), bc2 = R(1);
+      if (phase == PH_ADAM) {
+        bc1 = bias_corr(p.b1, R(gu + 1));
+        bc2 = bias_corr(p.b2, R(gu + 1));
+      }
+      for (int g = ls; g < p.n_su2; g += TPS) {
+        const Su2Meta* md = p.su2 + g;
+        R* cf = coef + 8 * g;
+        const int ax0 = md->axis[0], ax1 = md->axis[1], ax2 = md->axis[2];
+        const int pi0 = md->pidx[0], pi1 = md->pidx[1], pi2 = md->pidx[2];
+        R th0 = pi0 >= 0 ? ang[pi0] : R(md->cangle[0]);
+        R th1 = pi1 >= 0 ? ang[pi1] : R(md->cangle[1]);
+        R th2 = pi2 >= 0 ? ang[pi2] : R(md->cangle[2]);
+        if (phase != PH_COEF) {
+          const R sx = cf[0], sy = cf[1], sz = cf[2];
+          const R c2 = cf[4], s2 = cf[5], c3 = cf[6], s3 = cf[7];
+          const R C2 = c2 * c2 - s2 * s2, S2 = R(2) * c2 * s2;
+          const R C3 = c3 * c3 - s3 * s3, S3 = R(2) * c3 * s3;
+          if (pi2 >= 0)
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi2, sel3(ax2, sx, sy, sz), th2);
+          if (pi1 >= 0) {
+            R x = ax1 == 0, y = ax1 == 1, z = ax1 == 2;
+            rot_axis(ax2, C3, S3, x, y, z);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi1, x * sx + y * sy + z * sz, th1);
+          }
+          if (pi0 >= 0) {
+            R x = ax0 == 0, y = ax0 == 1, z = ax0 == 2;
+            rot_axis(ax1, C2, S2, x, y, z);
+            rot_axis(ax2, C3, S3, x, y, z);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi0, x * sx + y * sy + z * sz, th0);
+          }
+        }
+        if (!skip_coef) {
+          R c0 = R(1), s0 = R(0), c1 = R(1), s1 = R(0), c2 = R(1), s2 = R(0);
+          if (ax0 >= 0) sincos_r(th0 * R(0.5), s0, c0);
+          if (ax1 >= 0) sincos_r(th1 * R(0.5), s1, c1);
+          if (ax2 >= 0) sincos_r(th2 * R(0.5), s2, c2);
+          R ar, ai, br, bi, a2r, a2i, b2r, b2i;
+          su2_of(ax0, c0, s0, ar, ai, br, bi);
+          su2_of(ax1, c1, s1, a2r, a2i, b2r, b2i);
+          su2_mul(a2r, a2i, b2r, b2i, ar, ai, br, bi);
+          su2_of(ax2, c2, s2, a2r, a2i, b2r, b2i);
+          su2_mul(a2r, a2i, b2r, b2i, ar, ai, br, bi);
+          cf[0] = ar; cf[1] = ai; cf[2] = br; cf[3] = bi;
+          cf[4] = c1; cf[5] = s1; cf[6] = c2; cf[7] = s2;
+        }
+      }
+      for (int k = ls; k < p.n_cp; k += TPS) {
+        const CpMeta* md = p.cp + k;
+        R* cf = coef_cp + 2 * k;
+        const int pi = md->pidx;
+        const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
+                            (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
+        R th = pi >= 0 ? ang[pi] : R(md->cangle);
+        if (phase != PH_COEF && pi >= 0) {
+          R g = R(-2) * cf[0];
+          if (pen_on) {
+            R val, slope;
+            penalty_eval(p.pen, th, val, slope);
+            g = add_rn(g, mul_rn(p.pen.r, slope));
+          }
+          apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi, g, th);
+        }
+        if (!skip_coef) {
+          R s, c;
+          sincos_r(th, s, c);
+          cf[0] = c; cf[1] = s;
+          if (pen_on) {
+            R val, slope;
+            penalty_eval(p.pen, th, val, slope);
+            reg_part += val;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (it == p.nsteps) break;
+    V pr[NA], pi[NA];
     // ---------------- forward sweep: U e_col ----------------
 #pragma unroll
-    for (int j = 0; j < N; ++j) { pr[j] = T::onehot(j, col0); pi[j] = T::bc(R(0)); }
+    for (int r = 0; r < NA; ++r) { pr[r] = T::onehot((la << RB) | r, col0); pi[r] = T::bc(R(0)); }
     for (int i = 0; i < p.n_sched; ++i) {
       const uint32_t op = s_sched[i];
       const int kind = op & 15, q0 = (op >> 4) & 15, q1 = (op >> 8) & 15, slot = op >> 16;
       if (kind == S_SU2) {
         R ar, ai, br, bi;
         Vec4Load<R>::ld(coef + 8 * slot, ar, ai, br, bi);
-        CPF_Q_SWITCH(NQ, q0, (CO::template su2<Q>(pr, pi, ar, ai, br, bi)));
-      } else if (kind == S_CP) {
-        const R c = coef_cp[2 * slot], s = coef_cp[2 * slot + 1];
-        CPF_PAIR_SWITCH(NQ, q1, (CO::template phase<QA, QB>(pr, pi, c, s)));
-      } else if (kind == S_CZ) {
-        CPF_PAIR_SWITCH(NQ, q1, (CO::template negate<QA, QB>(pr, pi)));
+        const int bp = NQ - 1 - q0;
+        if (bp < RB) {
+          CPF_BP_SWITCH(RB, bp, (CO::template su2_reg<BP>(pr, pi, ar, ai, br, bi)));
+        } else {
+          CO::su2_lane(pr, pi, 1 << (bp - RB), ((la >> (bp - RB)) & 1) != 0, ar, ai, br, bi);
+        }
+      } else if (kind == S_CP || kind == S_CZ) {
+        const int pa = NQ - 1 - q0, pb = NQ - 1 - q1;
+        const int rm = (pa < RB ? 1 << pa : 0) | (pb < RB ? 1 << pb : 0);
+        const int lmask = (pa >= RB ? 1 << (pa - RB) : 0) | (pb >= RB ? 1 << (pb - RB) : 0);
+        const bool on = (la & lmask) == lmask;
+        R c = R(-1), s = R(0);
+        if (kind == S_CP) { c = coef_cp[2 * slot]; s = coef_cp[2 * slot + 1]; }
+        if (!on) { c = R(1); s = R(0); }
+        CPF_RM_SWITCH(RB, rm, (CO::template phase<RM>(pr, pi, c, s)));
       } else {
-        CPF_QQ_SWITCH(NQ, q0, q1, (CO::template cnot<QC, QT>(pr, pi)));
+        const int cpos = NQ - 1 - q0, tpos = NQ - 1 - q1;
+        if (tpos < RB) {
+          CPF_BP_SWITCH(RB, tpos, (CO::template cnot_reg<BP>(pr, pi, cpos, la)));
+        } else {
+          CO::cnot_lane(pr, pi, cpos, 1 << (tpos - RB), la);
+        }
       }
     }
 
     if (p.mode == M_UNITARY) {
       if (active) {
 #pragma unroll
-        for (int j = 0; j < N; ++j)
+        for (int r = 0; r < NA; ++r)
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
-            R* dst = p.u_out + ((b * N + j) * N + col0 + k) * 2;
-            dst[0] = T::get(pr[j], k); dst[1] = T::get(pi[j], k);
+            R* dst = p.u_out + ((b * N + ((la << RB) | r)) * N + col0 + k) * 2;
+            dst[0] = T::get(pr[r], k); dst[1] = T::get(pi[r], k);
           }
       }
       return;
     }
 
     // ---------------- loss and adjoint seed ----------------
-    V lr[N], li[N];
+    V lr[NA], li[NA];
     R loss = R(0), reg = R(0);
     if (p.mode == M_COTANGENT) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const R* src = p.cot + ((b * N + j) * N + col0) * 2;
+      for (int j = 0; j < NA; ++j) {
+        const R* src = p.cot + ((b * N + ((la << RB) | j)) * N + col0) * 2;
         lr[j] = T::make(src[0], CPT > 1 ? src[2] : R(0));
         li[j] = T::make(src[1], CPT > 1 ? src[3] : R(0));
       }
     } else if (p.loss_kind == CPF_LOSS_RELPHASE) {
       V acc = T::bc(R(0));
 #pragma unroll
-      for (int j = 0; j < N; ++j) {
+      for (int j = 0; j < NA; ++j) {
         const V vr = tv[2 * j], vi = tv[2 * j + 1];
         const V w = T::fma(vi, vi, T::mul(vr, vr));
         const V q = T::fma(pi[j], pi[j], T::mul(pr[j], pr[j]));
@@ -297,7 +305,7 @@ engine_kernel(const KParams<R> p) {
     } else {
       V trp = T::bc(R(0)), tip = trp, tin = trp;
 #pragma unroll
-      for (int j = 0; j < N; ++j) {
+      for (int j = 0; j < NA; ++j) {
         const V vr = tv[2 * j], vi = tv[2 * j + 1];
         trp = T::fma(vr, pr[j], trp); trp = T::fma(vi, pi[j], trp);
         tip = T::fma(vr, pi[j], tip); tin = T::fma(vi, pr[j], tin);
@@ -309,7 +317,7 @@ engine_kernel(const KParams<R> p) {
       loss = R(1) - mul_rn(ab, ab) / NN;
       const V a = T::bc(-tr / NN), bq = T::bc(ti / NN), nb = T::bc(-ti / NN);
 #pragma unroll
-      for (int j = 0; j < N; ++j) {
+      for (int j = 0; j < NA; ++j) {
         const V vr = tv[2 * j], vi = tv[2 * j + 1];
         lr[j] = T::fma(bq, vi, T::mul(a, vr));
         li[j] = T::fma(nb, vr, T::mul(a, vi));
@@ -352,45 +360,56 @@ engine_kernel(const KParams<R> p) {
         R* cf = coef + 8 * slot;
         R ar, ai, br, bi;
         Vec4Load<R>::ld(cf, ar, ai, br, bi);
+        const int bp = NQ - 1 - q0;
+        R sx = R(0), sy = R(0), sz = R(0);
+        if (bp < RB) {
+          if (has_param) CPF_BP_SWITCH(RB, bp, (CO::template pauli_reg<BP>(pr, pi, lr, li, sx, sy, sz)));
+          CPF_BP_SWITCH(RB, bp, {
+            CO::template su2_reg<BP>(pr, pi, ar, -ai, -br, -bi);
+            CO::template su2_reg<BP>(lr, li, ar, -ai, -br, -bi);
+          });
+        } else {
+          CO::bwd_lane(pr, pi, lr, li, 1 << (bp - RB), ((la >> (bp - RB)) & 1) != 0, has_param,
+                       ar, ai, br, bi, sx, sy, sz);
+        }
         if (has_param) {
-          R sx, sy, sz;
-          CPF_Q_SWITCH(NQ, q0, (CO::template pauli_sums<Q>(pr, pi, lr, li, sx, sy, sz)));
           sx = sample_sum<TPS>(sx); sy = sample_sum<TPS>(sy); sz = sample_sum<TPS>(sz);
           __syncwarp();
           if (ls == 0) { cf[0] = sx; cf[1] = sy; cf[2] = sz; }
         }
-        CPF_Q_SWITCH(NQ, q0, {
-          CO::template su2<Q>(pr, pi, ar, -ai, -br, -bi);
-          CO::template su2<Q>(lr, li, ar, -ai, -br, -bi);
-        });
-      } else if (kind == S_CP) {
+      } else if (kind == S_CP || kind == S_CZ) {
+        const int pa = NQ - 1 - q0, pb = NQ - 1 - q1;
+        const int rm = (pa < RB ? 1 << pa : 0) | (pb < RB ? 1 << pb : 0);
+        const int lmask = (pa >= RB ? 1 << (pa - RB) : 0) | (pb >= RB ? 1 << (pb - RB) : 0);
+        const bool on = (la & lmask) == lmask;
         R* cf = coef_cp + 2 * slot;
-        const R c = cf[0], s = cf[1];
+        R c = R(-1), s = R(0);
+        if (kind == S_CP) { c = cf[0]; s = cf[1]; }
+        if (!on) { c = R(1); s = R(0); }
         if (has_param) {
-          R s11;
-          CPF_PAIR_SWITCH(NQ, q1, (s11 = CO::template phase_sum<QA, QB>(pr, pi, lr, li)));
-          s11 = sample_sum<TPS>(s11);
+          R s11 = R(0);
+          CPF_RM_SWITCH(RB, rm, (s11 = CO::template phase_sum<RM>(pr, pi, lr, li)));
+          s11 = sample_sum<TPS>(on ? s11 : R(0));
           __syncwarp();
           if (ls == 0) cf[0] = s11;
         }
-        CPF_PAIR_SWITCH(NQ, q1, {
-          CO::template phase<QA, QB>(pr, pi, c, -s);
-          CO::template phase<QA, QB>(lr, li, c, -s);
-        });
-      } else if (kind == S_CZ) {
-        CPF_PAIR_SWITCH(NQ, q1, {
-          CO::template negate<QA, QB>(pr, pi);
-          CO::template negate<QA, QB>(lr, li);
+        CPF_RM_SWITCH(RB, rm, {
+          CO::template phase<RM>(pr, pi, c, -s);
+          CO::template phase<RM>(lr, li, c, -s);
         });
       } else {
-        CPF_QQ_SWITCH(NQ, q0, q1, {
-          CO::template cnot<QC, QT>(pr, pi);
-          CO::template cnot<QC, QT>(lr, li);
-        });
+        const int cpos = NQ - 1 - q0, tpos = NQ - 1 - q1;
+        if (tpos < RB) {
+          CPF_BP_SWITCH(RB, tpos, {
+            CO::template cnot_reg<BP>(pr, pi, cpos, la);
+            CO::template cnot_reg<BP>(lr, li, cpos, la);
+          });
+        } else {
+          CO::cnot_lane(pr, pi, cpos, 1 << (tpos - RB), la);
+          CO::cnot_lane(lr, li, cpos, 1 << (tpos - RB), la);
+        }
       }
     }
-    __syncwarp();
-    reg_part = param_phase(p.mode == M_ADAM ? PH_ADAM : PH_GRAD, gi, it == p.nsteps - 1);
     __syncwarp();
   }
 

@@ -1,4 +1,5 @@
 // float32 / complex64 instantiations of the engine (the reference's default x32 mode).
+// launch_one<R, NQ, RB, CPT, SINGLE>: RB register bits, NQ-RB lane bits, CPT packed columns.
 #include "launch.cuh"
 
 namespace cpf {
@@ -7,17 +8,17 @@ template <>
 int launch_engine<float>(const KParams<float>& p, int n, bool single, cudaStream_t st, std::string& err) {
   if (single) {
     switch (n) {
-      case 2: return launch_one<float, 2, 1, true>(p, st, err);
-      case 3: return launch_one<float, 3, 1, true>(p, st, err);
-      case 4: return launch_one<float, 4, 1, true>(p, st, err);
-      case 5: return launch_one<float, 5, 1, true>(p, st, err);
+      case 2: return launch_one<float, 2, 2, 1, true>(p, st, err);
+      case 3: return launch_one<float, 3, 2, 1, true>(p, st, err);
+      case 4: return launch_one<float, 4, 2, 1, true>(p, st, err);
+      case 5: return launch_one<float, 5, 3, 1, true>(p, st, err);
     }
   } else {
     switch (n) {
-      case 2: return launch_one<float, 2, 2, false>(p, st, err);
-      case 3: return launch_one<float, 3, 2, false>(p, st, err);
-      case 4: return launch_one<float, 4, 2, false>(p, st, err);
-      case 5: return launch_one<float, 5, 1, false>(p, st, err);
+      case 2: return launch_one<float, 2, 2, 2, false>(p, st, err);
+      case 3: return launch_one<float, 3, 2, 2, false>(p, st, err);
+      case 4: return launch_one<float, 4, 2, 2, false>(p, st, err);
+      case 5: return launch_one<float, 5, 4, 2, false>(p, st, err);
     }
   }
   err = "unsupported number of qubits";

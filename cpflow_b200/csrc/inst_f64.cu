@@ -1,4 +1,4 @@
-// double64 / complex128 instantiations of the engine (reference semantics in double).
+// float64 / complex128 instantiations of the engine (reference semantics in double).
 #include "launch.cuh"
 
 namespace cpf {
@@ -7,17 +7,17 @@ template <>
 int launch_engine<double>(const KParams<double>& p, int n, bool single, cudaStream_t st, std::string& err) {
   if (single) {
     switch (n) {
-      case 2: return launch_one<double, 2, 1, true>(p, st, err);
-      case 3: return launch_one<double, 3, 1, true>(p, st, err);
-      case 4: return launch_one<double, 4, 1, true>(p, st, err);
-      case 5: return launch_one<double, 5, 1, true>(p, st, err);
+      case 2: return launch_one<double, 2, 2, 1, true>(p, st, err);
+      case 3: return launch_one<double, 3, 2, 1, true>(p, st, err);
+      case 4: return launch_one<double, 4, 2, 1, true>(p, st, err);
+      case 5: return launch_one<double, 5, 3, 1, true>(p, st, err);
     }
   } else {
     switch (n) {
-      case 2: return launch_one<double, 2, 1, false>(p, st, err);
-      case 3: return launch_one<double, 3, 1, false>(p, st, err);
-      case 4: return launch_one<double, 4, 1, false>(p, st, err);
-      case 5: return launch_one<double, 5, 1, false>(p, st, err);
+      case 2: return launch_one<double, 2, 2, 1, false>(p, st, err);
+      case 3: return launch_one<double, 3, 2, 1, false>(p, st, err);
+      case 4: return launch_one<double, 4, 3, 1, false>(p, st, err);
+      case 5: return launch_one<double, 5, 5, 1, false>(p, st, err);
     }
   }
   err = "unsupported number of qubits";

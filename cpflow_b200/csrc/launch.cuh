@@ -19,9 +19,9 @@ inline int target_words(int n, int cpt, bool single) {
   return (single ? 1 : N / cpt) * (N + 1) * 2 * cpt;
 }
 
-template <typename R, int NQ, int CPT, bool SINGLE>
+template <typename R, int NQ, int RB, int CPT, bool SINGLE>
 int launch_one(KParams<R> p, cudaStream_t st, std::string& err) {
-  using C = Cfg<R, NQ, CPT, SINGLE>;
+  using C = Cfg<R, NQ, RB, CPT, SINGLE>;
   p.coef_stride = coef_stride_words(p.n_su2, p.n_cp);
   const size_t smem = (size_t)p.target_bytes + (size_t)((p.n_sched + 3) & ~3) * 4 +
                       (size_t)C::SPB * p.coef_stride * sizeof(R);
@@ -29,7 +29,7 @@ int launch_one(KParams<R> p, cudaStream_t st, std::string& err) {
     err = "program too large for the shared-memory coefficient store (" + std::to_string(smem) + " bytes)";
     return CPF_ERR_UNSUPPORTED;
   }
-  auto kern = engine_kernel<R, NQ, CPT, SINGLE>;
+  auto kern = engine_kernel<R, NQ, RB, CPT, SINGLE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
   const long long grid = (p.B + C::SPB - 1) / C::SPB;
@@ -43,7 +43,7 @@ int launch_one(KParams<R> p, cudaStream_t st, std::string& err) {
 
 // columns per thread chosen for each (dtype, n)
 template <typename R> constexpr int cpt_for(int n) { return 1; }
-template <> constexpr int cpt_for<float>(int n) { return n <= 4 ? 2 : 1; }
+template <> constexpr int cpt_for<float>(int n) { return 2; }
 
 template <typename R> int launch_engine(const KParams<R>& p, int n_qubits, bool single,
                                         cudaStream_t st, std::string& err);

@@ -70,11 +70,11 @@ std::string compile_program(Program& p) {
           if (op.param >= 0) p.is_cp_param[op.param] = 1;
           uint32_t slot = (uint32_t)p.cp.size();
           p.cp.push_back(m);
-          p.sched.push_back(pack_op(S_CP, lo, pair_index(n, lo, hi),
+          p.sched.push_back(pack_op(S_CP, lo, hi,
                                     op.param >= 0 ? FLAG_HAS_PARAM : 0, slot));
         } else if (op.kind == CPF_CZ) {
           if (op.param >= 0) { err << "op " << i << ": CZ takes no parameter"; return err.str(); }
-          p.sched.push_back(pack_op(S_CZ, lo, pair_index(n, lo, hi), 0, 0));
+          p.sched.push_back(pack_op(S_CZ, lo, hi, 0, 0));
         } else {
           if (op.param >= 0) { err << "op " << i << ": CX takes no parameter"; return err.str(); }
           p.sched.push_back(pack_op(S_CX, op.q0, op.q1, 0, 0));

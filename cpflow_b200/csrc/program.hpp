@@ -24,7 +24,7 @@ namespace cpf {
 enum SchedKind : uint32_t { S_SU2 = 0, S_CP = 1, S_CZ = 2, S_CX = 3 };
 
 // Packed schedule word: kind[0:4) | q0[4:8) | q1[8:12) | flags[12:16) | slot[16:32)
-// q1 of a CP/CZ op is the PAIR INDEX (lexicographic over q_lo < q_hi); for CX it is the target.
+// q0/q1 are qubit indices (CP/CZ: q0 < q1; CX: q0 control, q1 target).
 constexpr uint32_t FLAG_HAS_PARAM = 1u;
 inline uint32_t pack_op(uint32_t kind, uint32_t q0, uint32_t q1, uint32_t flags, uint32_t slot) {
   return kind | (q0 << 4) | (q1 << 8) | (flags << 12) | (slot << 16);
@@ -61,12 +61,6 @@ struct Program {
   mutable std::mutex mu;
   mutable std::unordered_map<int, DeviceProgram> dev;
 };
-
-inline int pair_index(int n, int a, int b) {  // a < b
-  int idx = 0;
-  for (int i = 0; i < a; ++i) idx += n - 1 - i;
-  return idx + (b - a - 1);
-}
 
 // Returns empty string on success, else an error message.
 std::string compile_program(Program& p);
