@@ -1,0 +1,146 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/cpflow_b200.h
+declares, host logic (program compilation, topology, ansatz layout, penalty table) agrees with
+the oracle.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import cpflow_oracle as O
+from cpflow_b200 import _lib as L
+from cpflow_b200 import ansatz as A
+from cpflow_b200 import topology as T
+from cpflow_b200 import penalty as PN
+from cpflow_b200 import gates as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cpflow_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cpf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/cpflow_b200.h but not exported"
+    assert set(syms) == set(L.EXPORTS), "ctypes table and header disagree"
+    assert lib.cpf_version() == 100
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(L.CpfOp) == 24
+    assert C.sizeof(L.CpfProgramInfo) == 32
+    assert C.sizeof(L.CpfAdamSpec) == 32
+    assert C.sizeof(L.CpfPenaltySpec) == 8 + 16 + 4 * 8 * L.MAX_SEGMENTS + 8
+    assert C.sizeof(L.CpfAdamBuffers) == 12 * 8
+
+
+def _create(lib, n, ops, P):
+    arr = (L.CpfOp * max(1, len(ops)))(*[L.CpfOp(*o) for o in ops])
+    h = C.c_void_p()
+    rc = lib.cpf_program_create(n, len(ops), arr, P, C.byref(h))
+    return rc, h
+
+
+def test_program_create_validation(lib):
+    rc, h = _create(lib, 3, [(L.RX, 0, -1, 0, 0.0), (L.CP, 0, 1, 1, 0.0)], 2)
+    assert rc == 0 and h.value
+    info = L.CpfProgramInfo()
+    assert lib.cpf_program_get_info(h, C.byref(info)) == 0
+    assert (info.n_qubits, info.n_params, info.n_ops, info.n_rotations, info.n_phase) == (3, 2, 2, 1, 1)
+    f, b = C.c_double(), C.c_double()
+    assert lib.cpf_eval_cost(h, L.LOSS_HS, L.F32, C.byref(f), C.byref(b)) == 0
+    assert f.value == 8 * 8 * (16 * 1 + 4 * 1 + 8) and b.value == 6 * 2 * 4 + 8
+    lib.cpf_program_destroy(h)
+    # errors: too many qubits, parameter reused, bad pair, bad kind, out-of-range param
+    for n, ops, P, code in [
+        (9, [(L.RX, 0, -1, 0, 0.0)], 1, -2),
+        (3, [(L.RX, 0, -1, 0, 0.0), (L.RY, 1, -1, 0, 0.0)], 1, -1),
+        (3, [(L.CP, 1, 1, 0, 0.0)], 1, -1),
+        (3, [(17, 0, -1, 0, 0.0)], 1, -1),
+        (3, [(L.RX, 0, -1, 5, 0.0)], 1, -1),
+        (3, [(L.CZ, 0, 1, 0, 0.0)], 1, -1),
+    ]:
+        rc, h = _create(lib, n, ops, P)
+        assert rc == code, (ops, rc)
+        assert not h.value
+        assert len(lib.cpf_last_error()) > 0
+
+
+def test_fusion_counts_for_cp_ansatz(lib):
+    """Surface rounds fuse to n SU(2) gates and every block to 2 (main.py:77-80, 122-124)."""
+    for n, layer, K, rg in [(4, T.chain_layer(4), 40, "xyz"), (3, T.connected_layer(3), 7, "xz"),
+                            (5, T.connected_layer(5), 23, "xyz")]:
+        anz = A.Ansatz(n, "cp", T.fill_layers(layer, K), rg)
+        rc, h = _create(lib, n, anz.ops, anz.num_angles)
+        assert rc == 0
+        info = L.CpfProgramInfo()
+        lib.cpf_program_get_info(h, C.byref(info))
+        assert info.n_rotations == 3 * n + 2 * len(rg) * K
+        assert info.n_phase == K
+        assert info.n_fused == n + 2 * K
+        assert info.n_sched == n + 3 * K
+        lib.cpf_program_destroy(h)
+
+
+@pytest.mark.parametrize("n,layer,K,rg", [(3, [[0, 1], [1, 2]], 12, "xyz"), (4, [[0, 1], [0, 2], [0, 3]], 40, "xyz"),
+                                           (4, [[3, 1], [2, 0]], 7, "zyx"), (5, T.connected_layer(5), 13, "xz")])
+def test_ansatz_layout_matches_oracle(n, layer, K, rg):
+    anz = A.Ansatz(n, "cp", T.fill_layers(layer, K), rg)
+    oanz = O.cp_ansatz(layer, K, rg)
+    assert anz.num_angles == oanz.num_angles == 3 * n + (2 * len(rg) + 1) * K
+    assert np.array_equal(anz.cp_mask, oanz.cp_mask)
+    assert [tuple(o) for o in anz.ops] == O.ansatz_program(oanz)
+
+
+def test_cz_ansatz_layout():
+    anz = A.Ansatz(3, "cz", T.fill_layers(T.chain_layer(3), 5), "xyz")
+    oanz = O.Ansatz(3, "cz", O.fill_layers(O.chain_layer(3), 5), "xyz")
+    assert anz.num_angles == oanz.num_angles == 9 + 6 * 5
+    assert [tuple(o) for o in anz.ops] == O.ansatz_program(oanz)
+    with pytest.raises(TypeError):
+        A.Ansatz(3, "iswap", T.fill_layers(T.chain_layer(3), 5))
+
+
+def test_topology_matches_reference_semantics():
+    assert T.connected_layer(3) == [[0, 1], [0, 2], [1, 2]]
+    assert T.chain_layer(4) == [[0, 1], [1, 2], [2, 3]]
+    assert T.fill_layers([[0, 1], [1, 2]], 5) == {"layers": [[[0, 1], [1, 2]], 2], "free": [[0, 1]]}
+    assert T.num_qubits_from_layer([[0, 3], [1, 2]]) == 4
+
+
+def test_penalty_table_matches_oracle():
+    import torch
+    pf = PN.make_regularization_function(PN.RegularizationOptions)
+    R = O.make_regularization_function()
+    x = np.concatenate([np.linspace(-7, 14, 4001), [0, np.pi, 2 * np.pi, np.pi / 2 - 0.05, 0.05]])
+    assert np.abs(pf(x) - R(torch.tensor(x)).numpy()).max() < 1e-12
+    assert len(pf.segments) <= L.MAX_SEGMENTS
+    l1 = PN.make_regularization_function(PN.RegularizationOptions(function="L1"))
+    assert np.array_equal(l1(x), np.abs(x))
+
+
+def test_toffoli_targets():
+    assert np.array_equal(G.u_toff3, O.toffoli_target(3).numpy())
+    assert np.array_equal(G.u_toff4, O.toffoli_target(4).numpy())
+    assert np.array_equal(G.u_toff5, O.toffoli_target(5).numpy())
+
+
+def test_product_path_has_no_cpu_fallback():
+    """Ops must fail loudly on CPU tensors instead of silently computing elsewhere."""
+    import torch
+    from cpflow_b200.engine import Program
+    anz = A.Ansatz(3, "cp", T.fill_layers(T.chain_layer(3), 4))
+    with pytest.raises(L.CpflowError):
+        anz.program.unitary(torch.zeros(2, anz.num_angles))
+    # and the package never imports the oracle
+    import cpflow_b200, pkgutil
+    for m in pkgutil.iter_modules(cpflow_b200.__path__):
+        src = open(os.path.join(cpflow_b200.__path__[0], m.name + ".py")).read() if not m.ispkg else ""
+        assert "oracle" not in src.replace("oracle restates", ""), m.name

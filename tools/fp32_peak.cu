@@ -2,6 +2,7 @@
 // Measures scalar FFMA, packed FFMA2 (fma.rn.f32x2), SHFL.BFLY and DFMA throughput.
 // The FFMA2 figure is the roofline denominator for the gate kernels (MEASURED_PEAKS.json has none).
 #include <cstdio>
+#include <string>
 #include <cuda_runtime.h>
 
 #define ILP 16
@@ -68,9 +69,17 @@ double run(const char* name, double flop_per_inner, int iters, int blocks_per_sm
   return rate;
 }
 
-int main() {
+int main(int argc, char** argv) {
   cudaError_t e = cudaFree(0);
   if (e != cudaSuccess) { printf("no gpu: %s\n", cudaGetErrorString(e)); return 1; }
+  const bool quick = argc > 1 && std::string(argv[1]) == "--quick";
+  if (quick) {  // roofline denominator only (bench.py)
+    for (int bps = 4; bps <= 8; bps *= 2) {
+      run<0>("ffma_flops", ILP * 2.0, 4000, bps);
+      run<1>("ffma2_flops", ILP * 4.0, 4000, bps);
+    }
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
+  }
   for (int bps = 2; bps <= 8; bps *= 2) {
     run<0>("ffma_flops", ILP * 2.0, 4000, bps);
     run<1>("ffma2_flops", ILP * 4.0, 4000, bps);
