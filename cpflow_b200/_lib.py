@@ -67,6 +67,7 @@ EXPORTS = {
                                C.POINTER(CpfAdamBuffers), C.c_void_p]),
     "cpf_count_cz": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cpf_cz_value": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "cpf_initial_angles": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int32, C.c_void_p, C.c_void_p]),
     "cpf_eval_cost": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -93,6 +93,30 @@ class Ansatz:
             u = u[0]
         return u if is_torch else u.cpu().numpy()
 
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st['_program'] = None
+        return st
+
+    def circuit(self, angles):
+        """Gate-list circuit of the template at `angles` (reference main.py:193-222, numeric angles
+        only): rz rx rz per qubit, then per block cp and the rotation letters on both qubits."""
+        from .circuit import Circuit
+        angles = np.asarray(angles, dtype=np.float64)
+        if angles.shape != (self.num_angles,):
+            raise ValueError(f"expected {self.num_angles} angles, got shape {angles.shape}")
+        name = {L.RX: 'rx', L.RY: 'ry', L.RZ: 'rz', L.CP: 'cp', L.CZ: 'cz', L.CX: 'cx'}
+        qc = Circuit(self.num_qubits)
+        for kind, q0, q1, p, c in self.ops:
+            a = float(angles[p]) if p >= 0 else c
+            if kind in (L.RX, L.RY, L.RZ):
+                qc.append(name[kind], [q0], [a])
+            elif kind == L.CP:
+                qc.append('cp', [q0, q1], [a])
+            else:
+                qc.append(name[kind], [q0, q1])
+        return qc
+
     def constrained(self, fixed_params, indices):
         """Program with parameters `indices` frozen at `fixed_params` — the device-side form of
         constrained_function(anz.unitary, ...) (reference cp_utils.py:100-108): returns

@@ -233,6 +233,20 @@ __global__ void count_cz_kernel(const cpf::CpMeta* cp, int n_cp, int P, long lon
   if (threadIdx.x == 0 && cz_out) cz_out[b] = cz;
 }
 
+// ---- elementwise cz_value (cp_utils.py:45-57) ----
+template <typename R>
+__global__ void cz_value_kernel(const R* angles, long long n, R threshold, int32_t* out) {
+  const R two_pi = R(2.0 * M_PI), pi = R(M_PI);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const R a = cpf::pymod(angles[i], two_pi);
+    int val = 2;
+    if (a < threshold || cpf::abs_r(a - two_pi) < threshold) val = 0;
+    else if (cpf::abs_r(a - pi) < threshold) val = 1;
+    out[i] = val;
+  }
+}
+
 // ---- jax 0.3.x threefry initial angles (main.py:541-548, cp_utils.py:13-42) ----
 __host__ __device__ inline void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
   const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
@@ -360,20 +374,22 @@ int cpf_program_get_info(const cpf_program* prog, cpf_program_info* info) {
 
 int cpf_unitary(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles, void* u_out,
                 void* stream) {
-  if (!prog || !angles || !u_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
-  if (batch == 0) return CPF_OK;
+  if (!prog || !u_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
   const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  if (!angles && p->n_params > 0) return fail(CPF_ERR_INVALID, "angles is NULL");
+  if (batch == 0) return CPF_OK;
   CPF_DISPATCH(dtype, (run_unitary<R>(p, batch, angles, u_out, (cudaStream_t)stream)));
 }
 
 int cpf_loss_grad(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_penalty_spec* penalty,
                   int32_t dtype, int64_t batch, const void* angles, void* loss_out, void* reg_out,
                   void* grad_out, void* stream) {
-  if (!prog || !angles || !loss_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  if (!prog || !loss_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  if (!angles && p->n_params > 0) return fail(CPF_ERR_INVALID, "angles is NULL");
   int rc = check_loss(loss);
   if (rc) return rc;
   if (batch == 0) return CPF_OK;
-  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
   CPF_DISPATCH(dtype, (run_loss_grad<R>(p, loss, penalty, batch, angles, loss_out, reg_out, grad_out,
                                         (cudaStream_t)stream)));
 }
@@ -425,6 +441,21 @@ int cpf_count_cz(const cpf_program* prog, int32_t dtype, int64_t batch, const vo
     count_cz_kernel<double><<<grid, block, 0, st>>>(d.cp, (int)p->cp.size(), p->n_params, batch,
                                                     (const double*)angles, threshold, cz_out,
                                                     (double*)projected, frozen);
+  else
+    return fail(CPF_ERR_INVALID, "unknown dtype");
+  CPF_CUDA(cudaGetLastError());
+  return CPF_OK;
+}
+
+int cpf_cz_value(int32_t dtype, int64_t n, const void* angles, double threshold, int32_t* out, void* stream) {
+  if (n < 0 || (n > 0 && (!angles || !out))) return fail(CPF_ERR_INVALID, "NULL argument / bad size");
+  if (n == 0) return CPF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  if (dtype == CPF_F32)
+    cz_value_kernel<float><<<grid, 256, 0, st>>>((const float*)angles, n, (float)threshold, out);
+  else if (dtype == CPF_F64)
+    cz_value_kernel<double><<<grid, 256, 0, st>>>((const double*)angles, n, threshold, out);
   else
     return fail(CPF_ERR_INVALID, "unknown dtype");
   CPF_CUDA(cudaGetLastError());

@@ -44,6 +44,10 @@ class Program:
         L.check(lib.cpf_program_get_info(self._h, C.byref(info)))
         self.info = {f[0]: getattr(info, f[0]) for f in L.CpfProgramInfo._fields_}
 
+    def __reduce__(self):
+        # handles are process-local: pickle the description and re-create on load
+        return (Program, (self.n_qubits, self.ops, self.n_params))
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and L._lib is not None:
@@ -179,6 +183,27 @@ class Loss:
         if key not in self._dev:
             self._dev[key] = torch.as_tensor(self.target, dtype=_CDT[dtype]).contiguous().to(device)
         return L.CpfLossSpec(self.KINDS[self.kind], self._dev[key].data_ptr())
+
+    def __getstate__(self):
+        return {"kind": self.kind, "target": self.target}
+
+    def __setstate__(self, st):
+        self.kind, self.target, self._dev = st["kind"], st["target"], {}
+
+    def __call__(self, u):
+        """Value of the loss at an explicit unitary `u` (host utility with the formulas of
+        matrix_utils.py:35-42 and the tutorial's state / relative-phase losses; the optimisation
+        itself never goes through here)."""
+        u = np.asarray(u.detach().cpu().numpy() if isinstance(u, torch.Tensor) else u)
+        n = u.shape[0]
+        if self.kind == "hs":
+            return float(1 - np.abs((u * self.target.conj()).sum()) ** 2 / n ** 2)
+        if self.kind == "state":
+            return float(1 - np.abs((self.target.conj() * u[:, 0]).sum()) ** 2)
+        return float(1 - (np.abs(self.target.conj() * u) ** 2).sum() / n)
+
+    def __repr__(self):
+        return f"Loss({self.kind!r}, target{tuple(self.target.shape)})"
 
 
 class Penalty:

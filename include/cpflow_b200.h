@@ -190,6 +190,11 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss,
 int cpf_count_cz(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles,
                  double threshold, int32_t* cz_out, void* projected, uint8_t* frozen, void* stream);
 
+/* out[n] (int32) = cz_value(angles[i], threshold) elementwise (cpflow/cp_utils.py:45-57): the number
+ * of CZ gates a CP gate with that angle costs (0 near 0/2pi, 1 near pi, else 2). */
+int cpf_cz_value(int32_t dtype, int64_t n, const void* angles, double threshold, int32_t* out,
+                 void* stream);
+
 /* Initial angles of Synthesize._generate_initial_angles (cpflow/main.py:541-548,
  * cpflow/cp_utils.py:13-42, cpflow/trigonometric_utils.py:35-38) with jax 0.3.x threefry
  * semantics: sample s of a batch of `total_samples` drawn from PRNGKey(seed).  Writes samples
