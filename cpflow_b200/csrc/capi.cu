@@ -374,31 +374,33 @@ int cpf_program_get_info(const cpf_program* prog, cpf_program_info* info) {
 
 int cpf_unitary(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles, void* u_out,
                 void* stream) {
-  if (!prog || !u_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  if (!prog || batch < 0) return fail(CPF_ERR_INVALID, "NULL program / bad batch");
+  if (batch == 0) return CPF_OK;
+  if (!u_out) return fail(CPF_ERR_INVALID, "u_out is NULL");
   const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
   if (!angles && p->n_params > 0) return fail(CPF_ERR_INVALID, "angles is NULL");
-  if (batch == 0) return CPF_OK;
   CPF_DISPATCH(dtype, (run_unitary<R>(p, batch, angles, u_out, (cudaStream_t)stream)));
 }
 
 int cpf_loss_grad(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_penalty_spec* penalty,
                   int32_t dtype, int64_t batch, const void* angles, void* loss_out, void* reg_out,
                   void* grad_out, void* stream) {
-  if (!prog || !loss_out || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
-  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
-  if (!angles && p->n_params > 0) return fail(CPF_ERR_INVALID, "angles is NULL");
+  if (!prog || batch < 0) return fail(CPF_ERR_INVALID, "NULL program / bad batch");
   int rc = check_loss(loss);
   if (rc) return rc;
   if (batch == 0) return CPF_OK;
+  if (!loss_out) return fail(CPF_ERR_INVALID, "loss_out is NULL");
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  if (!angles && p->n_params > 0) return fail(CPF_ERR_INVALID, "angles is NULL");
   CPF_DISPATCH(dtype, (run_loss_grad<R>(p, loss, penalty, batch, angles, loss_out, reg_out, grad_out,
                                         (cudaStream_t)stream)));
 }
 
 int cpf_adjoint_from_cotangent(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles,
                                const void* cotangent, void* grad_out, void* stream) {
-  if (!prog || !angles || !cotangent || !grad_out || batch < 0)
-    return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  if (!prog || batch < 0) return fail(CPF_ERR_INVALID, "NULL program / bad batch");
   if (batch == 0) return CPF_OK;
+  if (!angles || !cotangent || !grad_out) return fail(CPF_ERR_INVALID, "NULL argument");
   const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
   CPF_DISPATCH(dtype, (run_cotangent<R>(p, batch, angles, cotangent, grad_out, (cudaStream_t)stream)));
 }
@@ -410,6 +412,7 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_p
     return fail(CPF_ERR_INVALID, "NULL argument / negative size");
   int rc = check_loss(loss);
   if (rc) return rc;
+  if (batch == 0 || num_steps == 0) return CPF_OK;
   if (!buf->angles || !buf->m || !buf->v || !buf->best_params || !buf->best_regloss || !buf->best_reg ||
       !buf->init_regloss || !buf->init_reg)
     return fail(CPF_ERR_INVALID, "a required cpf_adam_buffers pointer is NULL");
@@ -424,8 +427,9 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_p
 
 int cpf_count_cz(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles, double threshold,
                  int32_t* cz_out, void* projected, uint8_t* frozen, void* stream) {
-  if (!prog || !angles || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / bad batch");
+  if (!prog || batch < 0) return fail(CPF_ERR_INVALID, "NULL program / bad batch");
   if (batch == 0) return CPF_OK;
+  if (!angles) return fail(CPF_ERR_INVALID, "angles is NULL");
   const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
   cpf::DeviceProgram d;
   int rc = device_program(p, &d);

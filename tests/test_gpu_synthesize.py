@@ -53,7 +53,9 @@ def test_mynimize_repeated_return_contract():
     assert isinstance(h, dict) and h["params"].shape == (20, anz.num_angles) and h["loss"].shape == (20,)
     assert np.array_equal(h["params"][0], a0[0])
     ph, lh = mynimize(pl, learning_rate=0.1, num_iterations=20, initial_params=a0[0], keep_history=True)
-    assert ph.shape == (20, anz.num_angles) and np.allclose(lh, h["regloss"])
+    h0 = mynimize_repeated(pl, learning_rate=0.1, num_iterations=20, initial_params_batch=a0[0], keep_history=True)
+    assert set(h0) == {"params", "loss"}
+    assert ph.shape == (20, anz.num_angles) and np.array_equal(lh, h0["loss"]) and np.array_equal(ph, h0["params"])
     # num_repeats without initial conditions; unitary_learn keys
     rr = mynimize_repeated(pl, num_repeats=3, num_iterations=5, keep_history=False)
     assert len(rr) == 3 and set(rr[0]) == {"params", "loss"}
