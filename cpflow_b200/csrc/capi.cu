@@ -1,6 +1,7 @@
 // C ABI of cpflow_b200 (include/cpflow_b200.h).  Plain pointers and sizes; no exceptions cross
 // the boundary.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -49,19 +50,58 @@ int device_program(const cpf::Program* prog, cpf::DeviceProgram* out) {
   return CPF_OK;
 }
 
+// decoded schedule for a kernel configuration with `rb` register bits, cached per device
+int device_decoded(const cpf::Program* prog, int rb, cpf::DeviceDecoded* out) {
+  if (rb < 0 || rb >= 8) return fail(CPF_ERR_UNSUPPORTED, "unsupported number of qubits");
+  int dev = 0;
+  CPF_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(prog->mu);
+  cpf::DeviceProgram& d = prog->dev[dev];
+  if (!d.has_dec[rb]) {
+    const cpf::DecodedSchedule ds = cpf::decode_schedule(*prog, rb);
+    cpf::DeviceDecoded dd;
+    const size_t no = ds.ops.size() * sizeof(uint32_t), nr = ds.red.size() * sizeof(uint16_t);
+    CPF_CUDA(cudaMalloc(&dd.ops, no ? no : 8));
+    CPF_CUDA(cudaMalloc(&dd.red, nr ? nr : 16));
+    if (no) CPF_CUDA(cudaMemcpy(dd.ops, ds.ops.data(), no, cudaMemcpyHostToDevice));
+    if (nr) CPF_CUDA(cudaMemcpy(dd.red, ds.red.data(), nr, cudaMemcpyHostToDevice));
+    dd.n_red = (int)(ds.red.size() / 8);
+    d.dec[rb] = dd;
+    d.has_dec[rb] = true;
+  }
+  *out = d.dec[rb];
+  return CPF_OK;
+}
+
 template <typename R>
-int fill_common(const cpf::Program* prog, cpf::KParams<R>& p, int64_t batch) {
+int fill_common(const cpf::Program* prog, cpf::KParams<R>& p, int64_t batch, bool single = false) {
   std::memset(&p, 0, sizeof(p));
   cpf::DeviceProgram d;
   int rc = device_program(prog, &d);
   if (rc) return rc;
-  p.sched = d.sched; p.n_sched = (int)prog->sched.size();
+  cpf::DeviceDecoded dd;
+  rc = device_decoded(prog, cpf::engine_rb<R>(prog->n_qubits, single), &dd);
+  if (rc) return rc;
+  p.dec = dd.ops; p.red = dd.red; p.n_red = dd.n_red;
+  p.n_sched = (int)prog->sched.size();
   p.su2 = d.su2; p.n_su2 = (int)prog->su2.size();
   p.cp = d.cp; p.n_cp = (int)prog->cp.size();
   p.P = prog->n_params; p.B = batch;
   p.pen.kind = CPF_PEN_NONE;
   p.nsteps = 1;
   return CPF_OK;
+}
+
+// layered templates run on their specialised kernel when one was compiled for the layer
+// (CPF_NO_LAYERED=1 forces the interpreter kernel: used by the tests to cover both)
+template <typename R>
+int launch_any(const cpf::KParams<R>& p, const cpf::Program* prog, bool single, cudaStream_t st,
+               std::string& err) {
+  const char* e = getenv("CPF_NO_LAYERED");
+  const bool no_layered = e && e[0] == '1';
+  int rc = CPF_OK;
+  if (prog->layered && !no_layered && cpf::launch_layered<R>(p, *prog, single, st, err, rc)) return rc;
+  return cpf::launch_engine<R>(p, prog->n_qubits, single, st, err);
 }
 
 template <typename R>
@@ -130,7 +170,7 @@ int run_unitary(const cpf::Program* prog, int64_t batch, const void* angles, voi
   p.mode = cpf::M_UNITARY;
   p.angles = (R*)angles; p.u_out = (R*)u_out;
   std::string err;
-  rc = cpf::launch_engine<R>(p, prog->n_qubits, false, st, err);
+  rc = launch_any<R>(p, prog, false, st, err);
   return rc ? fail(rc, err) : CPF_OK;
 }
 
@@ -139,9 +179,9 @@ int run_loss_grad(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf
                   int64_t batch, const void* angles, void* loss_out, void* reg_out, void* grad_out,
                   cudaStream_t st) {
   cpf::KParams<R> p;
-  int rc = fill_common(prog, p, batch);
-  if (rc) return rc;
   const bool single = loss->kind == CPF_LOSS_STATE;
+  int rc = fill_common(prog, p, batch, single);
+  if (rc) return rc;
   p.mode = cpf::M_LOSSGRAD;
   p.angles = (R*)angles; p.loss_out = (R*)loss_out; p.reg_out = (R*)reg_out; p.grad_out = (R*)grad_out;
   uint8_t* cp_pen = nullptr; R* packed = nullptr;
@@ -152,7 +192,7 @@ int run_loss_grad(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf
     if (e != cudaSuccess) rc = cuda_fail("cudaMemsetAsync(grad)", e);
   }
   std::string err;
-  if (!rc) { rc = cpf::launch_engine<R>(p, prog->n_qubits, single, st, err); if (rc) fail(rc, err); }
+  if (!rc) { rc = launch_any<R>(p, prog, single, st, err); if (rc) fail(rc, err); }
   if (packed) cudaFreeAsync(packed, st);
   if (cp_pen) cudaFreeAsync(cp_pen, st);
   return rc;
@@ -168,7 +208,7 @@ int run_cotangent(const cpf::Program* prog, int64_t batch, const void* angles, c
   p.angles = (R*)angles; p.cot = (const R*)cot; p.grad_out = (R*)grad_out;
   CPF_CUDA(cudaMemsetAsync(grad_out, 0, (size_t)batch * prog->n_params * sizeof(R), st));
   std::string err;
-  rc = cpf::launch_engine<R>(p, prog->n_qubits, false, st, err);
+  rc = launch_any<R>(p, prog, false, st, err);
   return rc ? fail(rc, err) : CPF_OK;
 }
 
@@ -177,9 +217,9 @@ int run_adam(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf_pena
              const cpf_adam_spec* adam, int64_t batch, int64_t step0, int64_t num_steps,
              const cpf_adam_buffers* buf, cudaStream_t st) {
   cpf::KParams<R> p;
-  int rc = fill_common(prog, p, batch);
-  if (rc) return rc;
   const bool single = loss->kind == CPF_LOSS_STATE;
+  int rc = fill_common(prog, p, batch, single);
+  if (rc) return rc;
   p.mode = cpf::M_ADAM;
   p.lr = (R)adam->lr; p.b1 = (R)adam->b1; p.b2 = (R)adam->b2; p.eps = (R)adam->eps;
   p.omb1 = (R)(1.0 - adam->b1); p.omb2 = (R)(1.0 - adam->b2);
@@ -192,7 +232,7 @@ int run_adam(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf_pena
   rc = fill_penalty(prog, pen, p, &cp_pen, st);
   if (!rc) rc = stage_target(prog, loss, p, single, &packed, st);
   std::string err;
-  if (!rc) { rc = cpf::launch_engine<R>(p, prog->n_qubits, single, st, err); if (rc) fail(rc, err); }
+  if (!rc) { rc = launch_any<R>(p, prog, single, st, err); if (rc) fail(rc, err); }
   if (packed) cudaFreeAsync(packed, st);
   if (cp_pen) cudaFreeAsync(cp_pen, st);
   return rc;
@@ -348,6 +388,8 @@ int cpf_program_destroy(cpf_program* prog) {
   for (auto& kv : p->dev) {
     cudaSetDevice(kv.first);
     cudaFree(kv.second.sched); cudaFree(kv.second.su2); cudaFree(kv.second.cp);
+    for (int r = 0; r < 8; ++r)
+      if (kv.second.has_dec[r]) { cudaFree(kv.second.dec[r].ops); cudaFree(kv.second.dec[r].red); }
   }
   cudaSetDevice(cur);
   delete p;

@@ -43,7 +43,8 @@ struct PenaltyT {
 
 template <typename R>
 struct KParams {
-  const uint32_t* sched; int n_sched;
+  const uint32_t* dec; int n_sched;   // decoded schedule: 2 words per op (program.hpp)
+  const uint16_t* red; int n_red;     // reduce tables: 8 offsets per group
   const Su2Meta* su2; int n_su2;
   const CpMeta* cp; int n_cp;
   const uint8_t* cp_pen;  // device [n_cp] or null: which CP params are penalised
@@ -70,6 +71,7 @@ template <> struct VT<float, 1> {
   static __device__ __forceinline__ V bc(float a) { return a; }
   static __device__ __forceinline__ V mul(V a, V b) { return a * b; }
   static __device__ __forceinline__ V fma(V a, V b, V c) { return fmaf(a, b, c); }
+  static __device__ __forceinline__ V sub(V a, V b) { return a - b; }
   static __device__ __forceinline__ float hsum(V a) { return a; }
   static __device__ __forceinline__ float get(V a, int) { return a; }
   static __device__ __forceinline__ V onehot(int j, int col0) { return j == col0 ? 1.f : 0.f; }
@@ -80,6 +82,7 @@ template <> struct VT<double, 1> {
   static __device__ __forceinline__ V bc(double a) { return a; }
   static __device__ __forceinline__ V mul(V a, V b) { return a * b; }
   static __device__ __forceinline__ V fma(V a, V b, V c) { return ::fma(a, b, c); }
+  static __device__ __forceinline__ V sub(V a, V b) { return a - b; }
   static __device__ __forceinline__ double hsum(V a) { return a; }
   static __device__ __forceinline__ double get(V a, int) { return a; }
   static __device__ __forceinline__ V onehot(int j, int col0) { return j == col0 ? 1.0 : 0.0; }
@@ -90,6 +93,7 @@ template <> struct VT<float, 2> {
   static __device__ __forceinline__ V bc(float a) { return make_float2(a, a); }
   static __device__ __forceinline__ V mul(V a, V b) { return __fmul2_rn(a, b); }
   static __device__ __forceinline__ V fma(V a, V b, V c) { return __ffma2_rn(a, b, c); }
+  static __device__ __forceinline__ V sub(V a, V b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
   static __device__ __forceinline__ float hsum(V a) { return a.x + a.y; }
   static __device__ __forceinline__ float get(V a, int k) { return k ? a.y : a.x; }
   static __device__ __forceinline__ V onehot(int j, int col0) {
@@ -291,9 +295,9 @@ struct Cols {
       yp = T::fma(lr[k], pr[j], yp); yn = T::fma(lr[j], pr[k], yn);
       yp = T::fma(li[k], pi[j], yp); yn = T::fma(li[j], pi[k], yn);
     }
-    sx = T::hsum(xp) - T::hsum(xn);
-    sy = T::hsum(yp) - T::hsum(yn);
-    sz = T::hsum(zp) - T::hsum(zn);
+    sx = T::hsum(T::sub(xp, xn));
+    sy = T::hsum(T::sub(yp, yn));
+    sz = T::hsum(T::sub(zp, zn));
   }
 
   // ---- lane-bit butterfly: new = A * mine + B * partner with per-lane (A, B) ----
@@ -340,8 +344,8 @@ struct Cols {
         xp = T::fma(lr[j], qi[j], xp); xn = T::fma(li[j], qr[j], xn);   // Im(conj(l) partner)
         yp = T::fma(lr[j], qr[j], yp); yp = T::fma(li[j], qi[j], yp);   // Re(conj(l) partner)
       }
-      const R z = T::hsum(zp) - T::hsum(zn), y = T::hsum(yp);
-      sx = T::hsum(xp) - T::hsum(xn);
+      const R z = T::hsum(T::sub(zp, zn)), y = T::hsum(yp);
+      sx = T::hsum(T::sub(xp, xn));
       sz = mybit ? -z : z;
       sy = mybit ? y : -y;
     }
@@ -399,7 +403,7 @@ struct Cols {
       if ((j & RM) != RM) continue;
       p = T::fma(lr[j], pi[j], p); n = T::fma(li[j], pr[j], n);
     }
-    return T::hsum(p) - T::hsum(n);
+    return T::hsum(T::sub(p, n));
   }
 };
 
@@ -443,10 +447,58 @@ struct Cfg {
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
 };
 
-// per-sample coefficient storage (R words): su2 gate g at [8g, 8g+8) =
+// per-sample coefficient storage (R words, program.hpp: coef_words): su2 gate g at [8g, 8g+8) =
 //   {alpha_r, alpha_i, beta_r, beta_i, c2, s2, c3, s3}; the adjoint sweep overwrites the first
-//   three words with the Pauli sums (Sx, Sy, Sz).  CP gate k at [8*n_su2 + 2k, +2) =
-//   {cos a, sin a}; overwritten with the |11> sum.
-__host__ __device__ inline int coef_words(int n_su2, int n_cp) { return 8 * n_su2 + 2 * n_cp; }
+//   three words with the Pauli sums (Sx, Sy, Sz).  Phase gate k (CP or CZ) at [8*n_su2 + 4k, +4) =
+//   {cos a, sin a, -, -}; word 0 is overwritten with the |11> sum.
+
+// Sum 8 per-thread partials over the TPS lanes of a sample with a transposing butterfly: the first
+// steps halve the number of live values (each lane sends the half its partner keeps), so 8 sums
+// over 32 lanes cost 4+2+1+1+1 = 9 shuffles instead of 40.  Afterwards the lanes whose low
+// (non-halving) bits are zero hold complete sums: lane bits (from the top) select the slot group.
+// dst[slot] is the word offset in the sample's coefficient store (0xffff: unused).
+template <int TPS> struct Red8 {
+  static constexpr int LOG = TPS >= 32 ? 5 : TPS >= 16 ? 4 : TPS >= 8 ? 3 : TPS >= 4 ? 2 : TPS >= 2 ? 1 : 0;
+  static constexpr int H = LOG < 3 ? LOG : 3;     // halving steps
+  static constexpr int CNT = 8 >> H;              // values left per lane
+};
+// After the call acc[0..CNT) of the lanes with `writer` hold the complete sums of slots
+// slot0 .. slot0+CNT-1.
+template <int TPS, typename R>
+__device__ __forceinline__ void reduce8(R (&acc)[8], int ls, int& slot0, bool& writer) {
+  constexpr int H = Red8<TPS>::H, CNT = Red8<TPS>::CNT;
+  slot0 = 0;
+#pragma unroll
+  for (int s = 0; s < H; ++s) {
+    const int m = TPS >> (s + 1);
+    const int cnt = 8 >> (s + 1);
+    const bool up = (ls & m) != 0;
+    if (up) slot0 += cnt;
+#pragma unroll
+    for (int k = 0; k < cnt; ++k) {
+      const R send = up ? acc[k] : acc[k + cnt];
+      const R keep = up ? acc[k + cnt] : acc[k];
+      acc[k] = keep + shfl_xor_r(send, m);
+    }
+  }
+#pragma unroll
+  for (int m = (TPS >> H) / 2; m >= 1; m >>= 1) {
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) acc[k] += shfl_xor_r(acc[k], m);
+  }
+  writer = (ls & ((TPS >> H) - 1)) == 0;
+}
+template <int TPS, typename R>
+__device__ __forceinline__ void reduce8_store(R (&acc)[8], const uint16_t* dst, R* coef, int ls) {
+  int slot0; bool writer;
+  reduce8<TPS>(acc, ls, slot0, writer);
+  if (writer) {
+#pragma unroll
+    for (int k = 0; k < Red8<TPS>::CNT; ++k) {
+      const uint32_t o = dst[slot0 + k];
+      if (o != 0xffffu) coef[o] = acc[k];
+    }
+  }
+}
 
 }  // namespace cpf

@@ -87,7 +87,304 @@ __host__ __device__ constexpr int min_blocks() {
   return state <= 32 ? 5 : (state <= 64 ? 4 : (state <= 128 ? 2 : 1));
 }
 
+// ---- compile-time dispatch of the decoded ops -------------------------------------------------
+#define CPF_SU2_CASE(I, ...) \
+  case DC_SU2_REG0 + I: if constexpr (RB > I) { constexpr int BP = I; __VA_ARGS__; } break;
+#define CPF_PH_CASE(I, ...) \
+  case DC_PHASE0 + I: if constexpr (I < (1 << RB)) { constexpr int RM = I; __VA_ARGS__; } break;
+// register masks with at most two bits set (a two-qubit gate)
+#define CPF_PH_CASES(...)                                                                          \
+  CPF_PH_CASE(0, __VA_ARGS__) CPF_PH_CASE(1, __VA_ARGS__) CPF_PH_CASE(2, __VA_ARGS__)               \
+  CPF_PH_CASE(3, __VA_ARGS__) CPF_PH_CASE(4, __VA_ARGS__) CPF_PH_CASE(5, __VA_ARGS__)               \
+  CPF_PH_CASE(6, __VA_ARGS__) CPF_PH_CASE(8, __VA_ARGS__) CPF_PH_CASE(9, __VA_ARGS__)               \
+  CPF_PH_CASE(10, __VA_ARGS__) CPF_PH_CASE(12, __VA_ARGS__) CPF_PH_CASE(16, __VA_ARGS__)            \
+  CPF_PH_CASE(17, __VA_ARGS__) CPF_PH_CASE(18, __VA_ARGS__) CPF_PH_CASE(20, __VA_ARGS__)            \
+  CPF_PH_CASE(24, __VA_ARGS__)
+
+// ------------------------------------------------------------------------------------------
+// Sweepers: how the forward and the adjoint sweep walk the gate schedule.
+//   InterpSweep  — general programs: one dispatch per decoded op (program.hpp: DecodedSchedule).
+//   LayerSweep   — layered templates (the CP / CZ ansatz of main.py:106-146): the blocks of one layer
+//                  are compile-time constants, so the sweeps are straight-line code with immediate
+//                  lane masks and coefficient offsets and no per-gate dispatch at all.
+// ------------------------------------------------------------------------------------------
 template <typename R, int NQ, int RB, int CPT, bool SINGLE>
+struct InterpSweep {
+  using C = Cfg<R, NQ, RB, CPT, SINGLE>;
+  using CO = Cols<R, RB, CPT>;
+  using T = VT<R, CPT>;
+  using V = typename T::V;
+  static constexpr int NA = C::NA, LB = C::LB, TPS = C::TPS;
+  static constexpr bool USES_SCHED = true;
+
+  static __device__ __forceinline__ void forward(const KParams<R>& p, R* coef, const uint2* s_dec, int la,
+                                                 V (&pr)[NA], V (&pi)[NA]) {
+#pragma unroll 1
+  for (int i = 0; i < p.n_sched; ++i) {
+    const uint2 d = s_dec[i];
+    R c0, c1, c2, c3;
+    Vec4Load<R>::ld(coef + (d.y & 0xffffu), c0, c1, c2, c3);
+    const int lm = (d.x >> 8) & 0xff;
+    switch (d.x & 0xffu) {
+      CPF_SU2_CASE(0, (CO::template su2_reg<BP>(pr, pi, c0, c1, c2, c3)))
+      CPF_SU2_CASE(1, (CO::template su2_reg<BP>(pr, pi, c0, c1, c2, c3)))
+      CPF_SU2_CASE(2, (CO::template su2_reg<BP>(pr, pi, c0, c1, c2, c3)))
+      CPF_SU2_CASE(3, (CO::template su2_reg<BP>(pr, pi, c0, c1, c2, c3)))
+      CPF_SU2_CASE(4, (CO::template su2_reg<BP>(pr, pi, c0, c1, c2, c3)))
+      case DC_SU2_LANE:
+        if constexpr (LB > 0) CO::su2_lane(pr, pi, lm, (la & lm) != 0, c0, c1, c2, c3);
+        break;
+      CPF_PH_CASES({
+        const bool on = (la & lm) == lm;
+        CO::template phase<RM>(pr, pi, on ? c0 : R(1), on ? c1 : R(0));
+      })
+      case DC_CX: {
+        const int cpos = lm & 15, tpos = lm >> 4;
+        if (tpos < RB) {
+          CPF_BP_SWITCH(RB, tpos, (CO::template cnot_reg<BP>(pr, pi, cpos, la)));
+        } else {
+          CO::cnot_lane(pr, pi, cpos, 1 << (tpos - RB), la);
+        }
+      } break;
+      default: break;
+    }
+  }
+
+  }
+
+  static __device__ __forceinline__ void backward(const KParams<R>& p, R* coef, const uint2* s_dec,
+                                                  const uint16_t* s_red, int la, int ls, V (&pr)[NA],
+                                                  V (&pi)[NA], V (&lr)[NA], V (&li)[NA]) {
+  // Per-thread partial gradient sums wait in `acc` (SU2: slots {0,1,2} or {3,4,5}; phase: 6 or 7)
+  // until the schedule says "reduce": one transposing butterfly then sums up to 8 of them.
+  R acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = R(0);
+#pragma unroll 1
+  for (int i = p.n_sched - 1; i >= 0; --i) {
+    const uint2 d = s_dec[i];
+    R c0, c1, c2, c3;
+    Vec4Load<R>::ld(coef + (d.y & 0xffffu), c0, c1, c2, c3);
+    const int lm = (d.x >> 8) & 0xff;
+    const bool hp = (d.x & (DF_PARAM << 16)) != 0;
+    const bool second = (d.x & (1u << 20)) != 0;   // acc base 3 (SU2) / 7 (phase)
+    R sx = R(0), sy = R(0), sz = R(0);
+    switch (d.x & 0xffu) {
+#define CPF_BWD_REG                                                              \
+{                                                                              \
+  if (hp) CO::template pauli_reg<BP>(pr, pi, lr, li, sx, sy, sz);              \
+  CO::template su2_reg<BP>(pr, pi, c0, -c1, -c2, -c3);                         \
+  CO::template su2_reg<BP>(lr, li, c0, -c1, -c2, -c3);                         \
+}
+      CPF_SU2_CASE(0, CPF_BWD_REG)
+      CPF_SU2_CASE(1, CPF_BWD_REG)
+      CPF_SU2_CASE(2, CPF_BWD_REG)
+      CPF_SU2_CASE(3, CPF_BWD_REG)
+      CPF_SU2_CASE(4, CPF_BWD_REG)
+#undef CPF_BWD_REG
+      case DC_SU2_LANE:
+        if constexpr (LB > 0)
+          CO::bwd_lane(pr, pi, lr, li, lm, (la & lm) != 0, hp, c0, c1, c2, c3, sx, sy, sz);
+        break;
+      CPF_PH_CASES({
+        const bool on = (la & lm) == lm;
+        if (hp) { sx = CO::template phase_sum<RM>(pr, pi, lr, li); sx = on ? sx : R(0); }
+        const R c = on ? c0 : R(1), s = on ? -c1 : R(0);
+        CO::template phase<RM>(pr, pi, c, s);
+        CO::template phase<RM>(lr, li, c, s);
+      })
+      case DC_CX: {
+        const int cpos = lm & 15, tpos = lm >> 4;
+        if (tpos < RB) {
+          CPF_BP_SWITCH(RB, tpos, {
+            CO::template cnot_reg<BP>(pr, pi, cpos, la);
+            CO::template cnot_reg<BP>(lr, li, cpos, la);
+          });
+        } else {
+          CO::cnot_lane(pr, pi, cpos, 1 << (tpos - RB), la);
+          CO::cnot_lane(lr, li, cpos, 1 << (tpos - RB), la);
+        }
+      } break;
+      default: break;
+    }
+    if (hp) {
+      if ((d.x & 0xffu) >= DC_PHASE0) {
+        if (second) acc[7] = sx; else acc[6] = sx;
+      } else if (second) {
+        acc[3] = sx; acc[4] = sy; acc[5] = sz;
+      } else {
+        acc[0] = sx; acc[1] = sy; acc[2] = sz;
+      }
+      if (d.x & (DF_REDUCE << 16)) {
+        __syncwarp();
+        reduce8_store<TPS>(acc, s_red + 8 * (d.y >> 16), coef, ls);
+      }
+    }
+  }
+  }
+};
+
+// Layered template: surface SU2 gate on every qubit (slot q), then K blocks; block k acts on the
+// qubit pair of position k % NBL of the layer: phase gate (slot k), then SU2 on the pair's lower
+// qubit (slot NQ + 2k) and on its higher qubit (slot NQ + 2k + 1).  LOQ / HIQ pack the layer's qubit
+// pairs, 4 bits per block.  program.cpp (detect_layered) renumbers the slots into this order.
+template <typename R, int NQ, int RB, int CPT, bool SINGLE, int NBL, unsigned long long LOQ,
+          unsigned long long HIQ>
+struct LayerSweep {
+  using C = Cfg<R, NQ, RB, CPT, SINGLE>;
+  using CO = Cols<R, RB, CPT>;
+  using T = VT<R, CPT>;
+  using V = typename T::V;
+  static constexpr int NA = C::NA, LB = C::LB, TPS = C::TPS;
+  static constexpr bool USES_SCHED = false;
+  static __host__ __device__ constexpr int lo_q(int j) { return (int)((LOQ >> (4 * j)) & 15); }
+  static __host__ __device__ constexpr int hi_q(int j) { return (int)((HIQ >> (4 * j)) & 15); }
+
+  // ---- single gates at a compile-time amplitude-bit position ----
+  template <int BP>
+  static __device__ __forceinline__ void su2_fwd(V (&re)[NA], V (&im)[NA], const R* cf, int la) {
+    R c0, c1, c2, c3;
+    Vec4Load<R>::ld(cf, c0, c1, c2, c3);
+    if constexpr (BP < RB) {
+      CO::template su2_reg<BP>(re, im, c0, c1, c2, c3);
+    } else {
+      constexpr int lm = 1 << (BP - RB);
+      CO::su2_lane(re, im, lm, (la & lm) != 0, c0, c1, c2, c3);
+    }
+  }
+  template <int BP>
+  static __device__ __forceinline__ void su2_bwd(V (&pr)[NA], V (&pi)[NA], V (&lr)[NA], V (&li)[NA],
+                                                 const R* cf, int la, R& sx, R& sy, R& sz) {
+    R c0, c1, c2, c3;
+    Vec4Load<R>::ld(cf, c0, c1, c2, c3);
+    if constexpr (BP < RB) {
+      CO::template pauli_reg<BP>(pr, pi, lr, li, sx, sy, sz);
+      CO::template su2_reg<BP>(pr, pi, c0, -c1, -c2, -c3);
+      CO::template su2_reg<BP>(lr, li, c0, -c1, -c2, -c3);
+    } else {
+      constexpr int lm = 1 << (BP - RB);
+      CO::bwd_lane(pr, pi, lr, li, lm, (la & lm) != 0, true, c0, c1, c2, c3, sx, sy, sz);
+    }
+  }
+  template <int PA, int PB> struct Ph {
+    static constexpr int RM = (PA < RB ? 1 << PA : 0) | (PB < RB ? 1 << PB : 0);
+    static constexpr int LM = (PA >= RB ? 1 << (PA - RB) : 0) | (PB >= RB ? 1 << (PB - RB) : 0);
+  };
+  template <int PA, int PB>
+  static __device__ __forceinline__ void phase_fwd(V (&re)[NA], V (&im)[NA], const R* cf, int la) {
+    using H = Ph<PA, PB>;
+    R c = cf[0], s = cf[1];
+    if constexpr (H::LM != 0) {
+      const bool on = (la & H::LM) == H::LM;
+      c = on ? c : R(1); s = on ? s : R(0);
+    }
+    CO::template phase<H::RM>(re, im, c, s);
+  }
+  template <int PA, int PB>
+  static __device__ __forceinline__ void phase_bwd(V (&pr)[NA], V (&pi)[NA], V (&lr)[NA], V (&li)[NA],
+                                                   const R* cf, int la, R& s11) {
+    using H = Ph<PA, PB>;
+    R c = cf[0], s = -cf[1];
+    s11 = CO::template phase_sum<H::RM>(pr, pi, lr, li);
+    if constexpr (H::LM != 0) {
+      const bool on = (la & H::LM) == H::LM;
+      c = on ? c : R(1); s = on ? s : R(0); s11 = on ? s11 : R(0);
+    }
+    CO::template phase<H::RM>(pr, pi, c, s);
+    CO::template phase<H::RM>(lr, li, c, s);
+  }
+
+  // ---- forward ----
+  template <int Q>
+  static __device__ __forceinline__ void surface_fwd(V (&pr)[NA], V (&pi)[NA], const R* coef, int la) {
+    if constexpr (Q < NQ) {
+      su2_fwd<NQ - 1 - Q>(pr, pi, coef + 8 * Q, la);
+      surface_fwd<Q + 1>(pr, pi, coef, la);
+    }
+  }
+  template <int J>
+  static __device__ __forceinline__ void blocks_fwd(int k0, int K, const R* cs, const R* cph, int la,
+                                                    V (&pr)[NA], V (&pi)[NA]) {
+    if constexpr (J < NBL) {
+      if (k0 + J >= K) return;
+      constexpr int PA = NQ - 1 - lo_q(J), PB = NQ - 1 - hi_q(J);
+      phase_fwd<PA, PB>(pr, pi, cph + 4 * J, la);
+      su2_fwd<PA>(pr, pi, cs + 16 * J, la);
+      su2_fwd<PB>(pr, pi, cs + 16 * J + 8, la);
+      blocks_fwd<J + 1>(k0, K, cs, cph, la, pr, pi);
+    }
+  }
+  static __device__ __forceinline__ void forward(const KParams<R>& p, R* coef, const uint2*, int la,
+                                                 V (&pr)[NA], V (&pi)[NA]) {
+    surface_fwd<0>(pr, pi, coef, la);
+    const int K = p.n_cp;
+    const R* cs = coef + 8 * NQ;
+    const R* cph = coef + 8 * p.n_su2;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += NBL) {
+      blocks_fwd<0>(k0, K, cs, cph, la, pr, pi);
+      cs += 16 * NBL; cph += 4 * NBL;
+    }
+  }
+
+  // ---- adjoint ----
+  // 7 sums of a block (or 6 of two surface gates) -> one transposing butterfly; the lane holding
+  // slot s stores it: slots 0-2 -> cfA[0..2], 3-5 -> cfB[0..2], 6 -> cph[0].
+  static __device__ __forceinline__ void reduce_store(R (&acc)[8], int ls, R* cfA, R* cfB, R* cph) {
+    int slot0; bool writer;
+    reduce8<TPS>(acc, ls, slot0, writer);
+    if (writer) {
+#pragma unroll
+      for (int k = 0; k < Red8<TPS>::CNT; ++k) {
+        const int s = slot0 + k;
+        R* dst = s < 3 ? cfA + s : (s < 6 ? cfB + (s - 3) : cph);
+        if (s < 3 || (s < 6 && cfB != nullptr) || (s == 6 && cph != nullptr)) *dst = acc[k];
+      }
+    }
+  }
+  template <int J>
+  static __device__ __forceinline__ void blocks_bwd(int k0, int K, R* cs, R* cph, int la, int ls,
+                                                    V (&pr)[NA], V (&pi)[NA], V (&lr)[NA], V (&li)[NA]) {
+    if constexpr (J >= 0) {
+      if (k0 + J < K) {
+        constexpr int PA = NQ - 1 - lo_q(J), PB = NQ - 1 - hi_q(J);
+        R acc[8];
+        acc[7] = R(0);
+        su2_bwd<PB>(pr, pi, lr, li, cs + 16 * J + 8, la, acc[3], acc[4], acc[5]);
+        su2_bwd<PA>(pr, pi, lr, li, cs + 16 * J, la, acc[0], acc[1], acc[2]);
+        phase_bwd<PA, PB>(pr, pi, lr, li, cph + 4 * J, la, acc[6]);
+        __syncwarp();
+        reduce_store(acc, ls, cs + 16 * J, cs + 16 * J + 8, cph + 4 * J);
+      }
+      blocks_bwd<J - 1>(k0, K, cs, cph, la, ls, pr, pi, lr, li);
+    }
+  }
+  template <int Q>
+  static __device__ __forceinline__ void surface_bwd(R* coef, int la, int ls, V (&pr)[NA], V (&pi)[NA],
+                                                     V (&lr)[NA], V (&li)[NA]) {
+    if constexpr (Q >= 0) {
+      R acc[8];
+      acc[3] = acc[4] = acc[5] = acc[6] = acc[7] = R(0);
+      su2_bwd<NQ - 1 - Q>(pr, pi, lr, li, coef + 8 * Q, la, acc[0], acc[1], acc[2]);
+      if constexpr (Q >= 1) su2_bwd<NQ - Q>(pr, pi, lr, li, coef + 8 * (Q - 1), la, acc[3], acc[4], acc[5]);
+      __syncwarp();
+      reduce_store(acc, ls, coef + 8 * Q, Q >= 1 ? coef + 8 * (Q - 1) : nullptr, nullptr);
+      surface_bwd<Q - 2>(coef, la, ls, pr, pi, lr, li);
+    }
+  }
+  static __device__ __forceinline__ void backward(const KParams<R>& p, R* coef, const uint2*, const uint16_t*,
+                                                  int la, int ls, V (&pr)[NA], V (&pi)[NA], V (&lr)[NA],
+                                                  V (&li)[NA]) {
+    const int K = p.n_cp;
+    R* cph0 = coef + 8 * p.n_su2;
+#pragma unroll 1
+    for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL)
+      blocks_bwd<NBL - 1>(k0, K, coef + 8 * NQ + 16 * k0, cph0 + 4 * k0, la, ls, pr, pi, lr, li);
+    surface_bwd<NQ - 1>(coef, la, ls, pr, pi, lr, li);
+  }
+};
+
+template <typename R, int NQ, int RB, int CPT, bool SINGLE, typename SW>
 __global__ void __launch_bounds__(Cfg<R, NQ, RB, CPT, SINGLE>::BLOCK, min_blocks<R, RB, CPT>())
 engine_kernel(const KParams<R> p) {
   using C = Cfg<R, NQ, RB, CPT, SINGLE>;
@@ -99,13 +396,14 @@ engine_kernel(const KParams<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   R* s_target = reinterpret_cast<R*>(smem_raw);
-  uint32_t* s_sched = reinterpret_cast<uint32_t*>(smem_raw + p.target_bytes);
-  R* s_coef = reinterpret_cast<R*>(s_sched + ((p.n_sched + 3) & ~3));
+  uint2* s_dec = reinterpret_cast<uint2*>(smem_raw + p.target_bytes);
+  uint16_t* s_red = reinterpret_cast<uint16_t*>(s_dec + ((p.n_sched + 1) & ~1));
+  R* s_coef = reinterpret_cast<R*>(s_red + 8 * p.n_red);
 
   const int tid = threadIdx.x;
   const bool need_target = p.mode == M_ADAM || p.mode == M_LOSSGRAD;
 
-  // ---- prologue: TMA-stage the target, copy the schedule ----
+  // ---- prologue: TMA-stage the target, copy the decoded schedule and the reduce tables ----
   if (need_target) {
     if (tid == 0) {
       mbar_init(&s_bar, 1);
@@ -117,7 +415,10 @@ engine_kernel(const KParams<R> p) {
       tma_bulk_g2s(s_target, p.target_packed, (uint32_t)p.target_bytes, &s_bar);
     }
   }
-  for (int i = tid; i < p.n_sched; i += C::BLOCK) s_sched[i] = p.sched[i];
+  if constexpr (SW::USES_SCHED) {
+    for (int i = tid; i < p.n_sched; i += C::BLOCK) s_dec[i] = reinterpret_cast<const uint2*>(p.dec)[i];
+    for (int i = tid; i < 8 * p.n_red; i += C::BLOCK) s_red[i] = p.red[i];
+  }
   __syncthreads();
   if (need_target) mbar_wait(&s_bar, 0);
 
@@ -202,7 +503,7 @@ engine_kernel(const KParams<R> p) {
       }
       for (int k = ls; k < p.n_cp; k += TPS) {
         const CpMeta* md = p.cp + k;
-        R* cf = coef_cp + 2 * k;
+        R* cf = coef_cp + 4 * k;
         const int pi = md->pidx;
         const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
                             (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
@@ -217,8 +518,8 @@ engine_kernel(const KParams<R> p) {
           apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi, g, th);
         }
         if (!skip_coef) {
-          R s, c;
-          sincos_r(th, s, c);
+          R s = R(0), c = R(-1);                 // CZ = diag(1,1,1,-1) exactly
+          if (!md->is_cz) sincos_r(th, s, c);
           cf[0] = c; cf[1] = s;
           if (pen_on) {
             R val, slope;
@@ -234,36 +535,7 @@ engine_kernel(const KParams<R> p) {
     // ---------------- forward sweep: U e_col ----------------
 #pragma unroll
     for (int r = 0; r < NA; ++r) { pr[r] = T::onehot((la << RB) | r, col0); pi[r] = T::bc(R(0)); }
-    for (int i = 0; i < p.n_sched; ++i) {
-      const uint32_t op = s_sched[i];
-      const int kind = op & 15, q0 = (op >> 4) & 15, q1 = (op >> 8) & 15, slot = op >> 16;
-      if (kind == S_SU2) {
-        R ar, ai, br, bi;
-        Vec4Load<R>::ld(coef + 8 * slot, ar, ai, br, bi);
-        const int bp = NQ - 1 - q0;
-        if (bp < RB) {
-          CPF_BP_SWITCH(RB, bp, (CO::template su2_reg<BP>(pr, pi, ar, ai, br, bi)));
-        } else {
-          CO::su2_lane(pr, pi, 1 << (bp - RB), ((la >> (bp - RB)) & 1) != 0, ar, ai, br, bi);
-        }
-      } else if (kind == S_CP || kind == S_CZ) {
-        const int pa = NQ - 1 - q0, pb = NQ - 1 - q1;
-        const int rm = (pa < RB ? 1 << pa : 0) | (pb < RB ? 1 << pb : 0);
-        const int lmask = (pa >= RB ? 1 << (pa - RB) : 0) | (pb >= RB ? 1 << (pb - RB) : 0);
-        const bool on = (la & lmask) == lmask;
-        R c = R(-1), s = R(0);
-        if (kind == S_CP) { c = coef_cp[2 * slot]; s = coef_cp[2 * slot + 1]; }
-        if (!on) { c = R(1); s = R(0); }
-        CPF_RM_SWITCH(RB, rm, (CO::template phase<RM>(pr, pi, c, s)));
-      } else {
-        const int cpos = NQ - 1 - q0, tpos = NQ - 1 - q1;
-        if (tpos < RB) {
-          CPF_BP_SWITCH(RB, tpos, (CO::template cnot_reg<BP>(pr, pi, cpos, la)));
-        } else {
-          CO::cnot_lane(pr, pi, cpos, 1 << (tpos - RB), la);
-        }
-      }
-    }
+    SW::forward(p, coef, s_dec, la, pr, pi);
 
     if (p.mode == M_UNITARY) {
       if (active) {
@@ -311,7 +583,7 @@ engine_kernel(const KParams<R> p) {
         tip = T::fma(vr, pi[j], tip); tin = T::fma(vi, pr[j], tin);
       }
       const R tr = sample_sum<TPS>(T::hsum(trp));
-      const R ti = sample_sum<TPS>(T::hsum(tip) - T::hsum(tin));
+      const R ti = sample_sum<TPS>(T::hsum(T::sub(tip, tin)));
       reg = sample_sum<TPS>(reg_part);
       const R ab = sqrt_r(tr * tr + ti * ti);
       loss = R(1) - mul_rn(ab, ab) / NN;
@@ -352,64 +624,7 @@ engine_kernel(const KParams<R> p) {
     }
 
     // ---------------- adjoint sweep ----------------
-    for (int i = p.n_sched - 1; i >= 0; --i) {
-      const uint32_t op = s_sched[i];
-      const int kind = op & 15, q0 = (op >> 4) & 15, q1 = (op >> 8) & 15, slot = op >> 16;
-      const bool has_param = (op >> 12) & FLAG_HAS_PARAM;
-      if (kind == S_SU2) {
-        R* cf = coef + 8 * slot;
-        R ar, ai, br, bi;
-        Vec4Load<R>::ld(cf, ar, ai, br, bi);
-        const int bp = NQ - 1 - q0;
-        R sx = R(0), sy = R(0), sz = R(0);
-        if (bp < RB) {
-          if (has_param) CPF_BP_SWITCH(RB, bp, (CO::template pauli_reg<BP>(pr, pi, lr, li, sx, sy, sz)));
-          CPF_BP_SWITCH(RB, bp, {
-            CO::template su2_reg<BP>(pr, pi, ar, -ai, -br, -bi);
-            CO::template su2_reg<BP>(lr, li, ar, -ai, -br, -bi);
-          });
-        } else {
-          CO::bwd_lane(pr, pi, lr, li, 1 << (bp - RB), ((la >> (bp - RB)) & 1) != 0, has_param,
-                       ar, ai, br, bi, sx, sy, sz);
-        }
-        if (has_param) {
-          sx = sample_sum<TPS>(sx); sy = sample_sum<TPS>(sy); sz = sample_sum<TPS>(sz);
-          __syncwarp();
-          if (ls == 0) { cf[0] = sx; cf[1] = sy; cf[2] = sz; }
-        }
-      } else if (kind == S_CP || kind == S_CZ) {
-        const int pa = NQ - 1 - q0, pb = NQ - 1 - q1;
-        const int rm = (pa < RB ? 1 << pa : 0) | (pb < RB ? 1 << pb : 0);
-        const int lmask = (pa >= RB ? 1 << (pa - RB) : 0) | (pb >= RB ? 1 << (pb - RB) : 0);
-        const bool on = (la & lmask) == lmask;
-        R* cf = coef_cp + 2 * slot;
-        R c = R(-1), s = R(0);
-        if (kind == S_CP) { c = cf[0]; s = cf[1]; }
-        if (!on) { c = R(1); s = R(0); }
-        if (has_param) {
-          R s11 = R(0);
-          CPF_RM_SWITCH(RB, rm, (s11 = CO::template phase_sum<RM>(pr, pi, lr, li)));
-          s11 = sample_sum<TPS>(on ? s11 : R(0));
-          __syncwarp();
-          if (ls == 0) cf[0] = s11;
-        }
-        CPF_RM_SWITCH(RB, rm, {
-          CO::template phase<RM>(pr, pi, c, -s);
-          CO::template phase<RM>(lr, li, c, -s);
-        });
-      } else {
-        const int cpos = NQ - 1 - q0, tpos = NQ - 1 - q1;
-        if (tpos < RB) {
-          CPF_BP_SWITCH(RB, tpos, {
-            CO::template cnot_reg<BP>(pr, pi, cpos, la);
-            CO::template cnot_reg<BP>(lr, li, cpos, la);
-          });
-        } else {
-          CO::cnot_lane(pr, pi, cpos, 1 << (tpos - RB), la);
-          CO::cnot_lane(lr, li, cpos, 1 << (tpos - RB), la);
-        }
-      }
-    }
+    SW::backward(p, coef, s_dec, s_red, la, ls, pr, pi, lr, li);
     __syncwarp();
   }
 

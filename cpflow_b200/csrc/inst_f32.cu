@@ -26,6 +26,16 @@ int launch_engine<float>(const KParams<float>& p, int n, bool single, cudaStream
 }
 
 template <>
+int engine_rb<float>(int n, bool single) {
+  if (single) {
+    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 3; }
+  } else {
+    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 4; }
+  }
+  return -1;
+}
+
+template <>
 int launch_pack_target<float>(const float* src, float* dst, int n, int cpt, bool single, cudaStream_t st) {
   pack_target_kernel<float><<<8, 256, 0, st>>>(src, dst, 1 << n, cpt, single ? 1 : 0);
   return cudaGetLastError() == cudaSuccess ? CPF_OK : CPF_ERR_CUDA;

@@ -25,6 +25,16 @@ int launch_engine<double>(const KParams<double>& p, int n, bool single, cudaStre
 }
 
 template <>
+int engine_rb<double>(int n, bool single) {
+  if (single) {
+    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 3; }
+  } else {
+    switch (n) { case 2: return 2; case 3: return 2; case 4: return 3; case 5: return 5; }
+  }
+  return -1;
+}
+
+template <>
 int launch_pack_target<double>(const double* src, double* dst, int n, int cpt, bool single, cudaStream_t st) {
   pack_target_kernel<double><<<8, 256, 0, st>>>(src, dst, 1 << n, cpt, single ? 1 : 0);
   return cudaGetLastError() == cudaSuccess ? CPF_OK : CPF_ERR_CUDA;

@@ -1,0 +1,47 @@
+// Specialised engine kernels for the standard layered templates (double): straight-line sweeps with
+// compile-time qubit pairs (engine_impl.cuh: LayerSweep).  Other layers run on the interpreter kernel.
+// Generated list: n, layer name, pairs packed 4 bits per block (lower qubits, higher qubits).
+#include "launch.cuh"
+
+namespace cpf {
+
+template <>
+bool launch_layered<double>(const KParams<double>& p, const Program& prog, bool single, cudaStream_t st,
+                           std::string& err, int& rc) {
+  if (single) return false;   // state preparation: interpreter kernel
+  const int n = prog.n_qubits, nb = prog.period;
+  const unsigned long long lo = prog.lo_pack, hi = prog.hi_pack;
+  // 2q chain [(0, 1)]
+  if (n == 2 && nb == 1 && lo == 0x0ull && hi == 0x1ull) {
+    rc = launch_one<double, 2, 2, 1, false, LayerSweep<double, 2, 2, 1, false, 1, 0x0ull, 0x1ull>>(p, st, err);
+    return true;
+  }
+  // 3q chain [(0, 1), (1, 2)]
+  if (n == 3 && nb == 2 && lo == 0x10ull && hi == 0x21ull) {
+    rc = launch_one<double, 3, 2, 1, false, LayerSweep<double, 3, 2, 1, false, 2, 0x10ull, 0x21ull>>(p, st, err);
+    return true;
+  }
+  // 3q connected [(0, 1), (0, 2), (1, 2)]
+  if (n == 3 && nb == 3 && lo == 0x100ull && hi == 0x221ull) {
+    rc = launch_one<double, 3, 2, 1, false, LayerSweep<double, 3, 2, 1, false, 3, 0x100ull, 0x221ull>>(p, st, err);
+    return true;
+  }
+  // 4q chain [(0, 1), (1, 2), (2, 3)]
+  if (n == 4 && nb == 3 && lo == 0x210ull && hi == 0x321ull) {
+    rc = launch_one<double, 4, 3, 1, false, LayerSweep<double, 4, 3, 1, false, 3, 0x210ull, 0x321ull>>(p, st, err);
+    return true;
+  }
+  // 4q star [(0, 1), (0, 2), (0, 3)]
+  if (n == 4 && nb == 3 && lo == 0x0ull && hi == 0x321ull) {
+    rc = launch_one<double, 4, 3, 1, false, LayerSweep<double, 4, 3, 1, false, 3, 0x0ull, 0x321ull>>(p, st, err);
+    return true;
+  }
+  // 4q connected [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+  if (n == 4 && nb == 6 && lo == 0x211000ull && hi == 0x332321ull) {
+    rc = launch_one<double, 4, 3, 1, false, LayerSweep<double, 4, 3, 1, false, 6, 0x211000ull, 0x332321ull>>(p, st, err);
+    return true;
+  }
+  return false;
+}
+
+}  // namespace cpf

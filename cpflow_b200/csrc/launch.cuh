@@ -19,17 +19,18 @@ inline int target_words(int n, int cpt, bool single) {
   return (single ? 1 : N / cpt) * (N + 1) * 2 * cpt;
 }
 
-template <typename R, int NQ, int RB, int CPT, bool SINGLE>
+template <typename R, int NQ, int RB, int CPT, bool SINGLE, typename SW = InterpSweep<R, NQ, RB, CPT, SINGLE>>
 int launch_one(KParams<R> p, cudaStream_t st, std::string& err) {
   using C = Cfg<R, NQ, RB, CPT, SINGLE>;
+  if (!SW::USES_SCHED) { p.n_sched = 0; p.n_red = 0; }
   p.coef_stride = coef_stride_words(p.n_su2, p.n_cp);
-  const size_t smem = (size_t)p.target_bytes + (size_t)((p.n_sched + 3) & ~3) * 4 +
+  const size_t smem = (size_t)p.target_bytes + (size_t)((p.n_sched + 1) & ~1) * 8 + (size_t)p.n_red * 16 +
                       (size_t)C::SPB * p.coef_stride * sizeof(R);
   if (smem > 227 * 1024) {
     err = "program too large for the shared-memory coefficient store (" + std::to_string(smem) + " bytes)";
     return CPF_ERR_UNSUPPORTED;
   }
-  auto kern = engine_kernel<R, NQ, RB, CPT, SINGLE>;
+  auto kern = engine_kernel<R, NQ, RB, CPT, SINGLE, SW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
   const long long grid = (p.B + C::SPB - 1) / C::SPB;
@@ -47,6 +48,12 @@ template <> constexpr int cpt_for<float>(int n) { return 2; }
 
 template <typename R> int launch_engine(const KParams<R>& p, int n_qubits, bool single,
                                         cudaStream_t st, std::string& err);
+// Specialised kernels for layered templates (inst_layer_*.cu).  Returns true and sets `rc` when a
+// kernel compiled for this layer exists; false means "use the interpreter kernel".
+template <typename R> bool launch_layered(const KParams<R>& p, const Program& prog, bool single,
+                                          cudaStream_t st, std::string& err, int& rc);
+// register bits of the kernel configuration launch_engine picks (selects the decoded schedule)
+template <typename R> int engine_rb(int n_qubits, bool single);
 template <typename R> int launch_pack_target(const R* src, R* dst, int n_qubits, int cpt, bool single,
                                              cudaStream_t st);
 

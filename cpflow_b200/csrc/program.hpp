@@ -39,14 +39,38 @@ struct Su2Meta {
 };
 struct CpMeta {
   int32_t pidx;      // -1 = constant angle
-  int32_t penalised; // 1 if the default penalty mask covers this parameter
+  int16_t penalised; // 1 if the default penalty mask covers this parameter
+  int16_t is_cz;     // 1: CZ = diag(1,1,1,-1) exactly (no angle)
   double cangle;
+};
+
+// ---- decoded schedule (what the kernels execute) -------------------------------------------
+// One 64-bit word per scheduled op, specialised for a kernel configuration (NQ qubits, RB register
+// bits): the kernel's inner loops do one jump-table dispatch per op and no index arithmetic.
+//   x: case[0:8) | lane mask[8:16) (SU2 on a lane bit: xor mask; phase: required lane bits;
+//      CX: control bit position [8:12), target bit position [12:16)) | flags[16:20) | acc base[20:24)
+//   y: coefficient offset in words [0:16) | reduce-table index [16:32)
+// Cases: 0..4 SU2 on register bit, 5 SU2 on a lane bit, 6 CX, 8 + rm: diagonal phase on the
+// amplitudes whose register bits `rm` are set.
+enum DecCase : uint32_t { DC_SU2_REG0 = 0, DC_SU2_LANE = 5, DC_CX = 6, DC_PHASE0 = 8 };
+constexpr uint32_t DF_PARAM = 1u;   // the adjoint sweep accumulates this op's gradient sums
+constexpr uint32_t DF_REDUCE = 2u;  // reduce and store the accumulated sums after this op
+struct DecodedSchedule {
+  std::vector<uint32_t> ops;   // 2 words per op (x, y)
+  std::vector<uint16_t> red;   // 8 destination offsets (words, 0xffff = unused) per reduce group
+};
+struct DeviceDecoded {
+  uint32_t* ops = nullptr;
+  uint16_t* red = nullptr;
+  int n_red = 0;
 };
 
 struct DeviceProgram {
   uint32_t* sched = nullptr;
   Su2Meta* su2 = nullptr;
   CpMeta* cp = nullptr;
+  DeviceDecoded dec[8];   // indexed by RB (register bits of the kernel configuration)
+  bool has_dec[8] = {false, false, false, false, false, false, false, false};
 };
 
 struct Program {
@@ -57,6 +81,11 @@ struct Program {
   std::vector<CpMeta> cp;
   std::vector<uint8_t> is_cp_param;  // [P]
   int n_rot = 0, n_phase = 0;
+  // layered-template structure (detect_layered): surface SU2 per qubit, then blocks
+  // [phase(lo,hi), SU2(lo), SU2(hi)] whose qubit pairs repeat with period `period`
+  bool layered = false;
+  int period = 0;
+  unsigned long long lo_pack = 0, hi_pack = 0;   // 4 bits per block of the layer
   // lazily created per-device copies
   mutable std::mutex mu;
   mutable std::unordered_map<int, DeviceProgram> dev;
@@ -64,5 +93,15 @@ struct Program {
 
 // Returns empty string on success, else an error message.
 std::string compile_program(Program& p);
+
+// words of per-sample coefficient storage: 8 per fused SU(2) gate, 4 per phase gate
+inline int coef_words(int n_su2, int n_cp) { return 8 * n_su2 + 4 * n_cp; }
+
+// Recognise the layered template structure and renumber the SU2 slots into its canonical order
+// (slot q: surface gate of qubit q; slots n+2k, n+2k+1: block k's lower / higher qubit).
+void detect_layered(Program& p);
+
+// Specialise the schedule for a kernel with `rb` register bits.
+DecodedSchedule decode_schedule(const Program& p, int rb);
 
 }  // namespace cpf

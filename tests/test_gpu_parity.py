@@ -345,3 +345,27 @@ def test_full_size_properties_c3(layer_name):
     lo_b, rg_b, _ = prog.loss_grad(st.best_params, Loss("hs", u_toff4), pen(0.001476), want_grad=False)
     assert float((lo_b + rg_b - st.best_regloss).abs().max()) < 1e-6
     assert float((rg_b - st.best_reg).abs().max()) < 1e-6
+
+
+def test_layered_and_interpreter_kernels_agree():
+    """Layered templates run on the specialised straight-line kernel (LayerSweep); the same program
+    forced onto the interpreter kernel (CPF_NO_LAYERED=1) must give the same numbers."""
+    import os
+    for n, layer, K, rg in [(4, chain_layer(4), 40, "xyz"), (4, [[0, 1], [0, 2], [0, 3]], 11, "xz"),
+                            (3, connected_layer(3), 7, "xyz"), (5, connected_layer(5), 13, "xyz"),
+                            (4, connected_layer(4), 9, "zx")]:
+        anz = Ansatz(n, "cp", fill_layers(layer, K), rg)
+        V = unitary_group.rvs(2 ** n, random_state=2)
+        for dt in (torch.float32, torch.float64):
+            a = torch.tensor(np.random.default_rng(K).uniform(0, 6.28, (21, anz.num_angles)), dtype=dt, device=DEV)
+            outs = []
+            for flag in ("0", "1"):
+                os.environ["CPF_NO_LAYERED"] = flag
+                lo, rg_, gr = anz.program.loss_grad(a, Loss("hs", V), pen())
+                st = anz.program.adam_state(a.clone())
+                anz.program.adam_run(st, Loss("hs", V), pen(), 0.1, 7)
+                outs.append((lo.clone(), gr.clone(), st.best_regloss.clone(), st.angles.clone()))
+            os.environ["CPF_NO_LAYERED"] = "0"
+            tol = 1e-12 if dt == torch.float64 else 2e-5
+            for x, y in zip(*outs):
+                assert float((x - y).abs().max()) <= tol * max(1.0, float(y.abs().max()))
