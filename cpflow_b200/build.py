@@ -18,8 +18,9 @@ OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcpflow_b200.so")
 
-SOURCES = ["program.cpp", "inst_f32.cu", "inst_f64.cu", "inst_layer_f32.cu", "inst_layer_f64.cu", "capi.cu"]
-HEADERS = ["program.hpp", "engine.cuh", "engine_impl.cuh", "launch.cuh",
+SOURCES = ["program.cpp", "inst_f32.cu", "inst_f64.cu", "inst_layer_f32.cu", "inst_layer_f64.cu",
+           "inst_heis_f32.cu", "inst_heis_f64.cu", "capi.cu"]
+HEADERS = ["program.hpp", "engine.cuh", "engine_impl.cuh", "launch.cuh", "heis_impl.cuh",
            os.path.join(ROOT, "include", "cpflow_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "cpflow_b200.h"
+#include "heis_impl.cuh"
 #include "launch.cuh"
 #include "program.hpp"
 
@@ -155,6 +156,54 @@ int stage_target(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KPara
   return CPF_OK;
 }
 
+// ---- Heisenberg-picture kernels (heis_impl.cuh): HS loss on layered templates ----
+// CPF_ENGINE=adjoint forces the state-adjoint kernels (tests cover both engines).
+template <typename R>
+bool use_heis(const cpf::Program* prog, const cpf_loss_spec* loss) {
+  if (loss->kind != CPF_LOSS_HS || !prog->layered) return false;
+  const char* e = getenv("CPF_ENGINE");
+  if (e && std::strcmp(e, "adjoint") == 0) return false;
+  const char* nl = getenv("CPF_NO_LAYERED");
+  if (nl && nl[0] == '1') return false;
+  cpf::KParams<R> dummy;
+  std::string err;
+  int rc = 0;
+  return cpf::launch_heis<R>(dummy, *prog, nullptr, err, rc, true);
+}
+
+template <typename R>
+int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams<R>& p, R** packed, R** aux,
+               cudaStream_t st) {
+  const int cpt = cpf::heis_cpt<R>(prog->n_qubits);
+  const int words = cpf::heis_target_words<R>(prog->n_qubits, cpt);
+  const size_t bytes = ((size_t)words * sizeof(R) + 15) & ~(size_t)15;
+  CPF_CUDA(cudaMallocAsync((void**)packed, bytes, st));
+  if (bytes != (size_t)words * sizeof(R)) CPF_CUDA(cudaMemsetAsync(*packed, 0, bytes, st));
+  int rc = cpf::launch_pack_target_heis<R>((const R*)loss->target, *packed, prog->n_qubits, cpt, st);
+  if (rc) return fail(rc, "pack_target_heis launch failed");
+  const size_t aux_bytes = (size_t)p.B * (prog->su2.empty() ? 1 : prog->su2.size()) * 4 * sizeof(R);
+  CPF_CUDA(cudaMallocAsync((void**)aux, aux_bytes, st));
+  p.target_packed = *packed;
+  p.target_bytes = (int)bytes;
+  p.loss_kind = loss->kind;
+  p.aux = *aux;
+  // rotation-axis pattern shared by the surface gates (slots < n) and by the block gates (the rest)
+  auto pattern = [&](size_t lo, size_t hi) {
+    int pat = -1;
+    for (size_t g = lo; g < hi && g < prog->su2.size(); ++g) {
+      const cpf::Su2Meta& md = prog->su2[g];
+      int q = 0;
+      for (int k = 0; k < 3; ++k) q |= (md.axis[k] < 0 ? 15 : md.axis[k]) << (4 * k);
+      if (pat == -1) pat = q;
+      else if (pat != q) return 0xffff;
+    }
+    return pat < 0 ? 0xffff : pat;
+  };
+  p.axp_surface = pattern(0, (size_t)prog->n_qubits);
+  p.axp_block = pattern((size_t)prog->n_qubits, prog->su2.size());
+  return CPF_OK;
+}
+
 int check_loss(const cpf_loss_spec* loss) {
   if (!loss || !loss->target) return fail(CPF_ERR_INVALID, "loss spec / target is NULL");
   if (loss->kind < CPF_LOSS_HS || loss->kind > CPF_LOSS_RELPHASE)
@@ -184,16 +233,22 @@ int run_loss_grad(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf
   if (rc) return rc;
   p.mode = cpf::M_LOSSGRAD;
   p.angles = (R*)angles; p.loss_out = (R*)loss_out; p.reg_out = (R*)reg_out; p.grad_out = (R*)grad_out;
-  uint8_t* cp_pen = nullptr; R* packed = nullptr;
+  uint8_t* cp_pen = nullptr; R* packed = nullptr; R* aux = nullptr;
+  const bool heis = use_heis<R>(prog, loss);
   rc = fill_penalty(prog, pen, p, &cp_pen, st);
-  if (!rc) rc = stage_target(prog, loss, p, single, &packed, st);
+  if (!rc) rc = heis ? stage_heis(prog, loss, p, &packed, &aux, st) : stage_target(prog, loss, p, single, &packed, st);
   if (!rc && grad_out) {
     cudaError_t e = cudaMemsetAsync(grad_out, 0, (size_t)batch * prog->n_params * sizeof(R), st);
     if (e != cudaSuccess) rc = cuda_fail("cudaMemsetAsync(grad)", e);
   }
   std::string err;
-  if (!rc) { rc = launch_any<R>(p, prog, single, st, err); if (rc) fail(rc, err); }
+  if (!rc) {
+    if (heis) cpf::launch_heis<R>(p, *prog, st, err, rc, false);
+    else rc = launch_any<R>(p, prog, single, st, err);
+    if (rc) fail(rc, err);
+  }
   if (packed) cudaFreeAsync(packed, st);
+  if (aux) cudaFreeAsync(aux, st);
   if (cp_pen) cudaFreeAsync(cp_pen, st);
   return rc;
 }
@@ -228,12 +283,18 @@ int run_adam(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf_pena
   p.best_params = (R*)buf->best_params; p.best_regloss = (R*)buf->best_regloss;
   p.best_reg = (R*)buf->best_reg; p.init_regloss = (R*)buf->init_regloss; p.init_reg = (R*)buf->init_reg;
   p.hist_params = (R*)buf->hist_params; p.hist_regloss = (R*)buf->hist_regloss; p.hist_len = buf->hist_len;
-  uint8_t* cp_pen = nullptr; R* packed = nullptr;
+  uint8_t* cp_pen = nullptr; R* packed = nullptr; R* aux = nullptr;
+  const bool heis = use_heis<R>(prog, loss);
   rc = fill_penalty(prog, pen, p, &cp_pen, st);
-  if (!rc) rc = stage_target(prog, loss, p, single, &packed, st);
+  if (!rc) rc = heis ? stage_heis(prog, loss, p, &packed, &aux, st) : stage_target(prog, loss, p, single, &packed, st);
   std::string err;
-  if (!rc) { rc = launch_any<R>(p, prog, single, st, err); if (rc) fail(rc, err); }
+  if (!rc) {
+    if (heis) cpf::launch_heis<R>(p, *prog, st, err, rc, false);
+    else rc = launch_any<R>(p, prog, single, st, err);
+    if (rc) fail(rc, err);
+  }
   if (packed) cudaFreeAsync(packed, st);
+  if (aux) cudaFreeAsync(aux, st);
   if (cp_pen) cudaFreeAsync(cp_pen, st);
   return rc;
 }

@@ -1,0 +1,716 @@
+// Heisenberg-picture engine kernel for the HS loss on layered templates (the Synthesize.static()
+// hot path: cost_HST of matrix_utils.py:35-42 over build_unitary of main.py:106-146).
+//
+// The adjoint sweep of engine_impl.cuh propagates two N x N complex states (phi, lambda) backwards:
+// 22 FMA per amplitude and fused gate plus a cross-lane reduction for every gradient entry.  Here
+// the backward sweep runs in the Heisenberg picture instead (tools/heisenberg_model.py is the numpy
+// statement of the same math, checked against the oracle by tests/test_heisenberg_model.py):
+//
+//   forward   Y = U V^dag, started from V^dag (staged in shared memory by TMA) instead of the identity:
+//             t = Tr(V^dag U) = Tr(Y), loss = 1 - |t|^2/N^2.  All n row bits of a column live in
+//             registers (CPT = 2 columns packed in float2 -> FFMA2), so the forward sweep has no
+//             shuffles at all: lane = column group.
+//   pivot     dL/dtheta_k = Tr(H_k sigma) with H_k = Herm(s Z_k), s = i conj(t)/N^2,
+//             Z_k = G_k..G_1 V^dag G_M..G_{k+1}, Z_M = Y.  H is Hermitian, so its Pauli coefficients
+//             h[x, z] = Re(i^{|x&z|} s W[x,z]),  W[x,z] = sum_r (-1)^{|z&r|} Y[r, r^x]
+//             are N^2 REAL numbers: one xor-shuffle all-to-all gathers the x-diagonals (lane = x >> PB)
+//             and a register-local Walsh-Hadamard transform over r produces W.
+//   backward  H_{k-1} = G_k^dag H_k G_k acts on h by real linear maps: a fused one-qubit gate rotates
+//             (h_X, h_Y, h_Z) of its qubit with the transpose of its SO(3) matrix (2.25 FMA per
+//             coefficient when the qubit's x bit is a register bit, 4 FMA + 0.5 SHFL when it is a lane
+//             bit), a CP gate rotates two difference pairs per (z1, z2) quad (2.5 FMA per coefficient).
+//             Every gradient entry is ONE coefficient of h (X: h[b,0], Y: h[b,b], Z: h[0,b]; CP:
+//             -(h[0,0]-h[0,b1]-h[0,b2]+h[0,b1|b2])/2): no reductions.
+//
+// Per sample and eval for C3 (n = 4, K = 40): ~300 k FMA-lane operations instead of ~680 k.
+#pragma once
+#include "engine_impl.cuh"
+
+namespace cpf {
+
+constexpr int HEIS_SU2_WORDS = 12;   // alpha,beta (fwd) -> M rows padded to float4 (bwd); pads 3,7,11 = S
+constexpr int HEIS_CP_WORDS = 4;     // cos, sin, r * penalty slope, - ; word 0 <- dL/da after the backward sweep
+
+inline int heis_coef_stride(int n_su2, int n_cp) {
+  int w = (HEIS_SU2_WORDS * n_su2 + HEIS_CP_WORDS * n_cp + 3) & ~3;
+  if (w == 0) w = 4;
+  if (((w / 4) & 1) == 0) w += 4;   // odd number of 16-byte groups: samples of a warp hit distinct banks
+  return w;
+}
+template <typename R> inline int heis_target_words(int n, int cpt) {
+  const int N = 1 << n;
+  return (N / cpt) * (N + 1) * 2 * cpt;
+}
+
+template <typename R, int NQ, int CPT>
+struct HCfg {
+  static constexpr int N = 1 << NQ;
+  static constexpr int PB = CPT == 2 ? 1 : 0;   // x bits of a thread held in registers
+  static constexpr int XR = 1 << PB;
+  static constexpr int TPS = N / CPT;           // threads per sample
+  // forward state registers: 2 * N * CPT words (x2 for double) -> register cap 128 (512 threads) or 255
+  static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? 512 : 256;
+  static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
+};
+
+template <typename V> struct AddV;
+template <> struct AddV<float> { static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+                                 static __device__ __forceinline__ float sub(float a, float b) { return a - b; } };
+template <> struct AddV<double> { static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+                                  static __device__ __forceinline__ double sub(double a, double b) { return a - b; } };
+template <> struct AddV<float2> {
+  static __device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+  static __device__ __forceinline__ float2 sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+};
+
+// Layered template (same slot order as LayerSweep, program.cpp: detect_layered): surface SU2 of qubit q
+// in slot q; block k = phase gate k on the qubit pair of position k % NBL, SU2 of the pair's lower
+// qubit in slot NQ + 2k, of its higher qubit in slot NQ + 2k + 1.
+template <typename R, int NQ, int CPT, int NBL, unsigned long long LOQ, unsigned long long HIQ>
+struct HeisSweep {
+  using CO = Cols<R, NQ, CPT>;
+  using T = VT<R, CPT>;
+  using V = typename T::V;
+  static constexpr int N = 1 << NQ, PB = CPT == 2 ? 1 : 0, XR = 1 << PB, TPS = N / CPT;
+  static constexpr int SW = HEIS_SU2_WORDS, CW = HEIS_CP_WORDS;
+  static __host__ __device__ constexpr int lo_q(int j) { return (int)((LOQ >> (4 * j)) & 15); }
+  static __host__ __device__ constexpr int hi_q(int j) { return (int)((HIQ >> (4 * j)) & 15); }
+
+  // ------------------------------- forward: row operations on Y -------------------------------
+  template <int BP>
+  static __device__ __forceinline__ void su2_fwd(V (&yr)[N], V (&yi)[N], const R* cf) {
+    R c0, c1, c2, c3;
+    Vec4Load<R>::ld(cf, c0, c1, c2, c3);
+    CO::template su2_reg<BP>(yr, yi, c0, c1, c2, c3);
+  }
+  template <int PA, int PB_>
+  static __device__ __forceinline__ void phase_fwd(V (&yr)[N], V (&yi)[N], const R* cf) {
+    CO::template phase<(1 << PA) | (1 << PB_)>(yr, yi, cf[0], cf[1]);
+  }
+  template <int Q>
+  static __device__ __forceinline__ void surface_fwd(V (&yr)[N], V (&yi)[N], const R* coef) {
+    if constexpr (Q < NQ) {
+      su2_fwd<NQ - 1 - Q>(yr, yi, coef + SW * Q);
+      surface_fwd<Q + 1>(yr, yi, coef);
+    }
+  }
+  template <int J>
+  static __device__ __forceinline__ void blocks_fwd(int k0, int K, const R* cs, const R* cph, V (&yr)[N],
+                                                    V (&yi)[N]) {
+    if constexpr (J < NBL) {
+      if (k0 + J >= K) return;
+      constexpr int PA = NQ - 1 - lo_q(J), PC = NQ - 1 - hi_q(J);
+      phase_fwd<PA, PC>(yr, yi, cph + CW * J);
+      su2_fwd<PA>(yr, yi, cs + 2 * SW * J);
+      su2_fwd<PC>(yr, yi, cs + 2 * SW * J + SW);
+      blocks_fwd<J + 1>(k0, K, cs, cph, yr, yi);
+    }
+  }
+  static __device__ __forceinline__ void forward(const KParams<R>& p, const R* coef, V (&yr)[N], V (&yi)[N]) {
+    surface_fwd<0>(yr, yi, coef);
+    const int K = p.n_cp;
+    const R* cs = coef + SW * NQ;
+    const R* cph = coef + SW * p.n_su2;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += NBL) {
+      __syncthreads();   // keep the warps of the CTA on the same instruction-cache lines
+      blocks_fwd<0>(k0, K, cs, cph, yr, yi);
+      cs += 2 * SW * NBL; cph += CW * NBL;
+    }
+  }
+
+  // ------------------ pivot: gather the x-diagonals, Walsh-Hadamard transform over r ------------------
+  // Before: lane l holds Y[r, l*CPT + k] (k = packed component).  Round d: every lane exchanges its rows
+  // r >> PB == d with lane l ^ d, in place.  After: lane m holds, in slot r, Y[r, ((m ^ (r>>PB)) << PB) | k],
+  // i.e. the element of diagonal x = (m << PB) | (k ^ (r & PB-bit)) at row r.
+  static __device__ __forceinline__ void gather_wht(V (&yr)[N], V (&yi)[N]) {
+#pragma unroll
+    for (int d = 1; d < TPS; ++d) {
+#pragma unroll
+      for (int r0 = 0; r0 < CPT; ++r0) {
+        const int r = d * CPT + r0;
+        yr[r] = ShflV<V>::x(yr[r], d);
+        yi[r] = ShflV<V>::x(yi[r], d);
+      }
+    }
+    if constexpr (CPT == 2) {
+      // butterfly over row bit 0: slot r0 = 0 holds (x0 = 0, x0 = 1), slot r0 = 1 holds (x0 = 1, x0 = 0)
+#pragma unroll
+      for (int r = 0; r < N; r += 2) {
+        const V ur = yr[r], wr = yr[r + 1], ui = yi[r], wi = yi[r + 1];
+        yr[r] = T::make(ur.x + wr.y, ur.y + wr.x); yr[r + 1] = T::make(ur.x - wr.y, ur.y - wr.x);
+        yi[r] = T::make(ui.x + wi.y, ui.y + wi.x); yi[r + 1] = T::make(ui.x - wi.y, ui.y - wi.x);
+      }
+    }
+#pragma unroll
+    for (int j = PB; j < NQ; ++j) {
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        if (r & (1 << j)) continue;
+        const V ar = yr[r], br = yr[r | (1 << j)], ai = yi[r], bi = yi[r | (1 << j)];
+        yr[r] = AddV<V>::add(ar, br); yr[r | (1 << j)] = AddV<V>::sub(ar, br);
+        yi[r] = AddV<V>::add(ai, bi); yi[r | (1 << j)] = AddV<V>::sub(ai, bi);
+      }
+    }
+  }
+
+  // ------------------------------- backward: real maps on h -------------------------------
+  // h[xr][z] is held packed over xr: hv[z] = (h[0][z], h[1][z]) for CPT = 2 (scalar for CPT = 1), so every map
+  // whose coefficients do not depend on xr issues as FFMA2; only gates on amplitude bit 0 (x bit = xr) are scalar.
+  static __device__ __forceinline__ V selv(bool pr, V a, V b) {
+    if constexpr (CPT == 2) return T::make(pr ? a.x : b.x, pr ? a.y : b.y);
+    else return pr ? a : b;
+  }
+  // Fused one-qubit gate on amplitude bit B.  cf: rows of M = R(G)^T, (X', Y', Z') = M (X, Y, Z), each row
+  // padded to 4 words; the pad words 3 / 7 / 11 receive the gradient sums (S_X, S_Y, S_Z) = entries of h.
+  template <int B>
+  static __device__ __forceinline__ void su2_bwd(V (&hv)[N], R* cf, int m) {
+    constexpr int BM = 1 << B;
+    if constexpr (B < PB) {
+      if (m == 0) { cf[3] = T::get(hv[0], 1); cf[7] = T::get(hv[BM], 1); cf[11] = T::get(hv[BM], 0); }
+    } else {
+      if (m == (1 << (B - PB))) { cf[3] = T::get(hv[0], 0); cf[7] = T::get(hv[BM], 0); }
+      if (m == 0) cf[11] = T::get(hv[BM], 0);
+    }
+    R m00, m01, m02, m10, m11, m12, m20, m21, m22, pad;
+    Vec4Load<R>::ld(cf, m00, m01, m02, pad);
+    Vec4Load<R>::ld(cf + 4, m10, m11, m12, pad);
+    Vec4Load<R>::ld(cf + 8, m20, m21, m22, pad);
+    if constexpr (B < PB) {
+      // x bit = xr: I = h[0][z], Z = h[0][z|1], X = h[1][z], Y = h[1][z|1]
+#pragma unroll
+      for (int z = 0; z < N; ++z) {
+        if (z & BM) continue;
+        const R X = T::get(hv[z], 1), Y = T::get(hv[z | BM], 1), Z = T::get(hv[z | BM], 0);
+        hv[z] = T::make(T::get(hv[z], 0), m00 * X + m01 * Y + m02 * Z);
+        hv[z | BM] = T::make(m20 * X + m21 * Y + m22 * Z, m10 * X + m11 * Y + m12 * Z);
+      }
+    } else {
+      // x bit is lane bit J: lanes with the bit clear hold (I, Z), lanes with it set hold (X, Y)
+      constexpr int J = B - PB;
+      const bool mb = ((m >> J) & 1) != 0;
+      const V ka = T::bc(mb ? m20 : R(0)), kb = T::bc(mb ? m21 : R(1));
+      const V k00 = T::bc(mb ? m00 : R(1)), k01 = T::bc(mb ? m01 : R(0)), k02 = T::bc(mb ? m02 : R(0));
+      const V k10 = T::bc(mb ? m10 : R(0)), k11 = T::bc(mb ? m11 : m22), k12 = T::bc(mb ? m12 : R(1));
+#pragma unroll
+      for (int z = 0; z < N; ++z) {
+        if (z & BM) continue;
+        const V e0 = hv[z], e1 = hv[z | BM];
+        const V send = T::fma(kb, e1, T::mul(ka, e0));
+        const V recv = ShflV<V>::x(send, 1 << J);
+        hv[z] = T::fma(k02, recv, T::fma(k01, e1, T::mul(k00, e0)));
+        hv[z | BM] = T::fma(k12, recv, T::fma(k11, e1, T::mul(k10, e0)));
+      }
+    }
+  }
+
+  // x bit of amplitude bit B (B >= PB) for this lane
+  template <int B>
+  static __device__ __forceinline__ bool xlane(int m) { return ((m >> (B - PB)) & 1) != 0; }
+
+  // CP / CZ gate on amplitude bits (B1, B2).  Quad e[z1][z2] at fixed x and other z bits; by the x bits of
+  // the two qubits: (1,0) pairs (e00,e01),(e10,e11); (0,1) pairs (e00,e10),(e01,e11); (1,1) pairs
+  // (e00,e11) and the SUM pair (e01,e10); (0,0) untouched.  The pair differences rotate by the CP angle.
+  template <typename E>
+  static __device__ __forceinline__ void cp_quad(E& e00, E& e01, E& e10, E& e11, bool isB, bool isC, E kcl, E ksl,
+                                                 E nsg) {
+    using O = VT<R, sizeof(E) == sizeof(R) ? 1 : 2>;
+    auto sel = [](bool pr, E a, E b) {
+      if constexpr (sizeof(E) == sizeof(R)) return pr ? a : b;
+      else return O::make(pr ? a.x : b.x, pr ? a.y : b.y);
+    };
+    E f01 = sel(isB, e10, sel(isC, e11, e01));
+    E f10 = sel(isB, e01, e10);
+    E f11 = sel(isC, e01, e11);
+    const E v1 = O::sub(e00, f01), v2 = O::fma(nsg, f11, f10);          // f10 - sg * f11
+    const E d1 = O::fma(ksl, v2, O::mul(kcl, v1));                      // kc v1 + ks v2
+    const E d2 = O::sub(O::mul(kcl, v2), O::mul(ksl, v1));              // kc v2 - ks v1
+    e00 = AddV<E>::add(e00, d1); f01 = O::sub(f01, d1);
+    f10 = AddV<E>::add(f10, d2); f11 = O::fma(nsg, d2, f11);            // f11 - sg * d2
+    e01 = sel(isB, f10, sel(isC, f11, f01));
+    e10 = sel(isB, f01, f10);
+    e11 = sel(isC, f01, f11);
+  }
+  template <int B1, int B2>
+  static __device__ __forceinline__ void phase_bwd(V (&hv)[N], R* cf, int m) {
+    constexpr int M1 = 1 << B1, M2 = 1 << B2;
+    const R c = cf[0], s = cf[1];
+    const R g11 = R(-0.5) * ((T::get(hv[0], 0) - T::get(hv[M1], 0)) - (T::get(hv[M2], 0) - T::get(hv[M1 | M2], 0)));
+    __syncwarp();
+    if (m == 0) cf[0] = g11;
+    const R kc = R(0.5) * (c - R(1)), ks = R(0.5) * s;
+    if constexpr (B1 >= PB && B2 >= PB) {
+      // both x bits are lane bits: one group per lane, packed arithmetic over xr
+      const bool x1 = xlane<B1>(m), x2 = xlane<B2>(m);
+      const bool isB = !x1 && x2, isC = x1 && x2, on = x1 || x2;
+      const V kcl = T::bc(on ? kc : R(0)), ksl = T::bc(on ? ks : R(0)), nsg = T::bc(isC ? R(1) : R(-1));
+#pragma unroll
+      for (int z = 0; z < N; ++z) {
+        if (z & (M1 | M2)) continue;
+        cp_quad<V>(hv[z], hv[z | M2], hv[z | M1], hv[z | M1 | M2], isB, isC, kcl, ksl, nsg);
+      }
+    } else {
+      // one of the bits is amplitude bit 0, whose x bit is the packed component xr: scalar per component
+      constexpr int BL = B1 >= PB ? B1 : B2;          // the lane bit
+      const bool xl = xlane<BL>(m);
+#pragma unroll
+      for (int xr = 0; xr < XR; ++xr) {
+        const bool x1 = B1 >= PB ? xl : xr != 0, x2 = B2 >= PB ? xl : xr != 0;
+        const bool isB = !x1 && x2, isC = x1 && x2, on = x1 || x2;
+        const R kcl = on ? kc : R(0), ksl = on ? ks : R(0), nsg = isC ? R(1) : R(-1);
+#pragma unroll
+        for (int z = 0; z < N; ++z) {
+          if (z & (M1 | M2)) continue;
+          R e00 = T::get(hv[z], xr), e01 = T::get(hv[z | M2], xr), e10 = T::get(hv[z | M1], xr),
+            e11 = T::get(hv[z | M1 | M2], xr);
+          cp_quad<R>(e00, e01, e10, e11, isB, isC, kcl, ksl, nsg);
+          setc(hv[z], xr, e00); setc(hv[z | M2], xr, e01); setc(hv[z | M1], xr, e10); setc(hv[z | M1 | M2], xr, e11);
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ void setc(V& v, int k, R x) {
+    if constexpr (CPT == 2) { if (k) v.y = x; else v.x = x; }
+    else v = x;
+  }
+
+  template <int J>
+  static __device__ __forceinline__ void blocks_bwd(int k0, int K, R* cs, R* cph, int m, V (&h)[N]) {
+    if constexpr (J >= 0) {
+      if (k0 + J < K) {
+        constexpr int PA = NQ - 1 - lo_q(J), PC = NQ - 1 - hi_q(J);
+        su2_bwd<PC>(h, cs + 2 * SW * J + SW, m);
+        su2_bwd<PA>(h, cs + 2 * SW * J, m);
+        phase_bwd<PA, PC>(h, cph + CW * J, m);
+      }
+      blocks_bwd<J - 1>(k0, K, cs, cph, m, h);
+    }
+  }
+  template <int Q>
+  static __device__ __forceinline__ void surface_bwd(R* coef, int m, V (&h)[N]) {
+    if constexpr (Q >= 0) {
+      su2_bwd<NQ - 1 - Q>(h, coef + SW * Q, m);
+      surface_bwd<Q - 1>(coef, m, h);
+    }
+  }
+  static __device__ __forceinline__ void backward(const KParams<R>& p, R* coef, int m, V (&h)[N]) {
+    const int K = p.n_cp;
+    R* cph0 = coef + SW * p.n_su2;
+#pragma unroll 1
+    for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL) {
+      __syncthreads();
+      blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, cph0 + CW * k0, m, h);
+    }
+    surface_bwd<NQ - 1>(coef, m, h);
+  }
+};
+
+// SO(3) matrix of G = [[alpha, -conj(beta)], [beta, conj(alpha)]] = w - i (x sx + y sy + z sz), stored
+// transposed (M = R^T) in rows of 4 words; the pad words are left alone (they carry the gradient sums).
+template <typename R>
+__device__ __forceinline__ void heis_su2_to_so3(R* cf) {
+  const R w = cf[0], z = -cf[1], y = cf[2], x = -cf[3];
+  const R xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  cf[0] = R(1) - R(2) * (yy + zz); cf[1] = R(2) * (xy + wz); cf[2] = R(2) * (xz - wy);
+  cf[4] = R(2) * (xy - wz); cf[5] = R(1) - R(2) * (xx + zz); cf[6] = R(2) * (yz + wx);
+  cf[8] = R(2) * (xz + wy); cf[9] = R(2) * (yz - wx); cf[10] = R(1) - R(2) * (xx + yy);
+}
+
+// ------------------------------------------------------------------------------------------
+// update / coefficient phase helpers (per gate, executed by the gate's owner thread)
+// ------------------------------------------------------------------------------------------
+template <typename R>
+struct UpdCtx {
+  int phase;            // PH_COEF / PH_ADAM / PH_GRAD
+  bool active;          // this thread's sample exists
+  bool store_best;      // the step being finished improved on the best regloss: keep its parameters
+  bool skip_coef;       // last pass: no new coefficients
+  long long b, gu;      // sample, step being finished
+  R bc1, bc2, ibc1, ibc2;
+  R* ang; R* mom; R* vel; const uint8_t* frz;
+};
+
+// sin/cos for the parameter phase, inlined so the three evaluations of a fused gate interleave
+__device__ __forceinline__ void sincos_inl(float x, float& s, float& c) {
+  if (fabsf(x) > 48000.f) { sincos_slow_f(x, &s, &c); return; }
+  const float j = rintf(x * 0.636619747f);
+  float r = fmaf(j, -1.57079601e+00f, x);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const int q = __float2int_rn(j);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  cp = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const float ss = (q & 1) ? cp : sp;
+  const float cc = (q & 1) ? sp : cp;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
+}
+__device__ __forceinline__ void sincos_inl(double x, double& s, double& c) { sincos_r(x, s, c); }
+
+// optax scale_by_adam + scale(-lr) (optimization.py:22-23).  double: exact IEEE sequence of the oracle.
+// float: reciprocal bias corrections, approximate sqrt and division (<= 2 ulp each; the reference's XLA
+// arithmetic is not bit-reproducible either, the Adam parity tests bound the drift).
+__device__ __forceinline__ void adam_inl(const KParams<double>& p, const UpdCtx<double>& u, double g, double& th,
+                                         double& mu, double& nu) {
+  mu = add_rn(mul_rn(p.omb1, g), mul_rn(p.b1, mu));
+  nu = add_rn(mul_rn(p.omb2, mul_rn(g, g)), mul_rn(p.b2, nu));
+  const double mu_hat = mu / u.bc1, nu_hat = nu / u.bc2;
+  th = add_rn(th, mul_rn(-p.lr, mu_hat / add_rn(sqrt(nu_hat), p.eps)));
+}
+__device__ __forceinline__ void adam_inl(const KParams<float>& p, const UpdCtx<float>& u, float g, float& th,
+                                         float& mu, float& nu) {
+  mu = add_rn(mul_rn(p.omb1, g), mul_rn(p.b1, mu));
+  nu = add_rn(mul_rn(p.omb2, mul_rn(g, g)), mul_rn(p.b2, nu));
+  const float mu_hat = mu * u.ibc1, nu_hat = nu * u.ibc2;
+  float rt;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(rt) : "f"(nu_hat));
+  th = add_rn(th, mul_rn(-p.lr, __fdividef(mu_hat, add_rn(rt, p.eps))));
+}
+
+// one parameter: gradient sink (loss_grad mode) or best-parameter bookkeeping + Adam step
+template <typename R>
+__device__ __forceinline__ void heis_apply(const KParams<R>& p, const UpdCtx<R>& u, int pi, R g, R& th, R mu, R nu) {
+  const int P = p.P;
+  if (u.phase == PH_GRAD) {
+    if (u.active) p.grad_out[u.b * P + pi] = g;
+    return;
+  }
+  // th is still the pre-update parameter of the step being finished (optimization.py:70-73)
+  if (u.store_best && u.active) p.best_params[u.b * P + pi] = th;
+  if (u.frz && u.frz[pi]) return;
+  adam_inl(p, u, g, th, mu, nu);
+  if (u.active) {
+    u.mom[pi] = mu; u.vel[pi] = nu; u.ang[pi] = th;
+    if (p.hist_params && u.gu + 1 < p.hist_len)
+      p.hist_params[(u.b * p.hist_len + u.gu + 1) * P + pi] = th;
+  }
+}
+
+// Fused one-qubit gate: finish the step (chain rule through the fusion, Adam), then the new (alpha, beta).
+// AX* >= 0: compile-time rotation axes (the selects fold away); AX0 == -2: axes from the gate metadata.
+template <typename R, int AX0, int AX1, int AX2>
+__device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, const Su2Meta* md,
+                                                R* cf, R* ax) {
+  const int ax0 = AX0 == -2 ? md->axis[0] : AX0;
+  const int ax1 = AX0 == -2 ? md->axis[1] : AX1;
+  const int ax2 = AX0 == -2 ? md->axis[2] : AX2;
+  const int pi0 = md->pidx[0], pi1 = md->pidx[1], pi2 = md->pidx[2];
+  R th0, th1, th2;
+  if (pi0 >= 0) th0 = u.ang[pi0]; else th0 = R(md->cangle[0]);
+  if (pi1 >= 0) th1 = u.ang[pi1]; else th1 = R(md->cangle[1]);
+  if (pi2 >= 0) th2 = u.ang[pi2]; else th2 = R(md->cangle[2]);
+  if (u.phase != PH_COEF) {
+    // all loads of the gate first: the three Adam updates then run back to back
+    R mu0 = R(0), nu0 = R(0), mu1 = R(0), nu1 = R(0), mu2 = R(0), nu2 = R(0);
+    if (u.phase == PH_ADAM && u.gu > 0) {
+      if (pi0 >= 0) { mu0 = u.mom[pi0]; nu0 = u.vel[pi0]; }
+      if (pi1 >= 0) { mu1 = u.mom[pi1]; nu1 = u.vel[pi1]; }
+      if (pi2 >= 0) { mu2 = u.mom[pi2]; nu2 = u.vel[pi2]; }
+    }
+    const R sx = cf[3], sy = cf[7], sz = cf[11];
+    R c2, s2, c3, s3;
+    Vec4Load<R>::ld(ax, c2, s2, c3, s3);
+    const R C2 = c2 * c2 - s2 * s2, S2 = R(2) * c2 * s2;
+    const R C3 = c3 * c3 - s3 * s3, S3 = R(2) * c3 * s3;
+    R x1 = ax1 == 0, y1 = ax1 == 1, z1 = ax1 == 2;
+    rot_axis(ax2, C3, S3, x1, y1, z1);
+    R x0 = ax0 == 0, y0 = ax0 == 1, z0 = ax0 == 2;
+    rot_axis(ax1, C2, S2, x0, y0, z0);
+    rot_axis(ax2, C3, S3, x0, y0, z0);
+    const R g2 = sel3(ax2, sx, sy, sz);
+    const R g1 = x1 * sx + y1 * sy + z1 * sz;
+    const R g0 = x0 * sx + y0 * sy + z0 * sz;
+    if (pi2 >= 0) heis_apply(p, u, pi2, g2, th2, mu2, nu2);
+    if (pi1 >= 0) heis_apply(p, u, pi1, g1, th1, mu1, nu1);
+    if (pi0 >= 0) heis_apply(p, u, pi0, g0, th0, mu0, nu0);
+  }
+  if (!u.skip_coef) {
+    R c0 = R(1), s0 = R(0), c1 = R(1), s1 = R(0), c2 = R(1), s2 = R(0);
+    if (ax0 >= 0) sincos_inl(th0 * R(0.5), s0, c0);
+    if (ax1 >= 0) sincos_inl(th1 * R(0.5), s1, c1);
+    if (ax2 >= 0) sincos_inl(th2 * R(0.5), s2, c2);
+    R ar, ai, br, bi, a2r, a2i, b2r, b2i;
+    su2_of(ax0, c0, s0, ar, ai, br, bi);
+    su2_of(ax1, c1, s1, a2r, a2i, b2r, b2i);
+    su2_mul(a2r, a2i, b2r, b2i, ar, ai, br, bi);
+    su2_of(ax2, c2, s2, a2r, a2i, b2r, b2i);
+    su2_mul(a2r, a2i, b2r, b2i, ar, ai, br, bi);
+    cf[0] = ar; cf[1] = ai; cf[2] = br; cf[3] = bi;
+    if (u.active) { ax[0] = c1; ax[1] = s1; ax[2] = c2; ax[3] = s2; }
+  }
+}
+// packed axes of a gate class: a0 | a1 << 4 | a2 << 8 (15 = unused slot); 0xffff = not uniform
+constexpr int AXP_ZXZ = 2 | (0 << 4) | (2 << 8);
+constexpr int AXP_XYZ = 0 | (1 << 4) | (2 << 8);
+constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
+template <typename R>
+__device__ __forceinline__ void heis_su2_update_any(int axp, const KParams<R>& p, const UpdCtx<R>& u,
+                                                    const Su2Meta* md, R* cf, R* ax) {
+  if (axp == AXP_XYZ) heis_su2_update<R, 0, 1, 2>(p, u, md, cf, ax);
+  else if (axp == AXP_ZXZ) heis_su2_update<R, 2, 0, 2>(p, u, md, cf, ax);
+  else if (axp == AXP_XZ) heis_su2_update<R, 0, 2, -1>(p, u, md, cf, ax);
+  else heis_su2_update<R, -2, -2, -2>(p, u, md, cf, ax);
+}
+
+// The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
+// sample slots are used (heis_geometry spreads the batch evenly over SMs and rounds).
+template <typename R, int NQ, int CPT, typename SWP>
+__global__ void __launch_bounds__(HCfg<R, NQ, CPT>::MAXT, 1)
+heis_kernel(const KParams<R> p) {
+  using C = HCfg<R, NQ, CPT>;
+  using T = VT<R, CPT>;
+  using V = typename T::V;
+  constexpr int N = C::N, TPS = C::TPS, PB = C::PB, XR = C::XR;
+  constexpr int SW = HEIS_SU2_WORDS, CW = HEIS_CP_WORDS;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  R* s_target = reinterpret_cast<R*>(smem_raw);
+  R* s_coef = reinterpret_cast<R*>(smem_raw + p.target_bytes);
+
+  const int tid = threadIdx.x;
+  // ---- prologue: TMA-stage V^dag (packed by pack_target_heis_kernel) ----
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar, (uint32_t)p.target_bytes);
+    tma_bulk_g2s(s_target, p.target_packed, (uint32_t)p.target_bytes, &s_bar);
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+
+  const int sl = tid / TPS;   // sample within the block
+  const int m = tid % TPS;    // lane within the sample: column group (forward), x >> PB (backward)
+  const long long b_raw = (long long)blockIdx.x * p.spb + sl;
+  const bool active = sl < p.spb && b_raw < p.B;
+  const long long b = active ? b_raw : p.B - 1;
+  const int P = p.P;
+  // idle sample slots (block size rounded up to whole warps) replay sample B-1 in one spare store
+  R* coef = s_coef + (size_t)(sl < p.spb ? sl : p.spb) * p.coef_stride;
+  R* coef_cp = coef + SW * p.n_su2;
+  const V* tv = reinterpret_cast<const V*>(s_target) + 2 * (size_t)m * (N + 1);
+
+  R* ang = p.angles + b * P;
+  R* mom = p.m ? p.m + b * P : nullptr;
+  R* vel = p.v ? p.v + b * P : nullptr;
+  R* aux = p.aux + b * (long long)p.n_su2 * 4;
+  const uint8_t* frz = p.freeze ? p.freeze + b * P : nullptr;
+  const R NN = R(N) * R(N);
+
+  R best = R(0), best_reg_v = R(0);
+  bool improved_prev = false;
+  if (p.mode == M_ADAM && p.step0 > 0) { best = p.best_regloss[b]; best_reg_v = p.best_reg[b]; }
+
+  for (int it = 0; it <= p.nsteps; ++it) {
+    const long long gi = p.step0 + it;
+    const int phase = it == 0 ? PH_COEF : (p.mode == M_ADAM ? PH_ADAM : PH_GRAD);
+    // ---------------- parameter phase (a sample's threads split the gates) ----------------
+    R reg_part = R(0);
+    {
+      UpdCtx<R> u;
+      u.phase = phase; u.active = active; u.b = b; u.gu = gi - 1;
+      u.store_best = improved_prev && p.mode == M_ADAM && phase == PH_ADAM;
+      u.skip_coef = it == p.nsteps;
+      u.ang = ang; u.mom = mom; u.vel = vel; u.frz = frz;
+      u.bc1 = u.bc2 = u.ibc1 = u.ibc2 = R(1);
+      if (phase == PH_ADAM) {
+        u.bc1 = bias_corr(p.b1, R(u.gu + 1));
+        u.bc2 = bias_corr(p.b2, R(u.gu + 1));
+        u.ibc1 = R(1) / u.bc1; u.ibc2 = R(1) / u.bc2;
+      }
+      // surface gates (slots < NQ) and block gates (the rest) each share one axis pattern in the templates
+      for (int g = m; g < NQ && g < p.n_su2; g += TPS)
+        heis_su2_update_any(p.axp_surface, p, u, p.su2 + g, coef + SW * g, aux + 4 * g);
+      for (int g = NQ + m; g < p.n_su2; g += TPS)
+        heis_su2_update_any(p.axp_block, p, u, p.su2 + g, coef + SW * g, aux + 4 * g);
+      for (int k = m; k < p.n_cp; k += TPS) {
+        const CpMeta* md = p.cp + k;
+        R* cf = coef_cp + CW * k;
+        const int pi = md->pidx;
+        const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
+                            (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
+        R th;
+        if (pi >= 0) th = ang[pi]; else th = R(md->cangle);
+        if (phase != PH_COEF && pi >= 0) {
+          R mu = R(0), nu = R(0);
+          if (phase == PH_ADAM && u.gu > 0) { mu = mom[pi]; nu = vel[pi]; }
+          // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
+          heis_apply(p, u, pi, add_rn(cf[0], cf[2]), th, mu, nu);
+        }
+        if (!u.skip_coef) {
+          R s = R(0), c = R(-1);                 // CZ = diag(1,1,1,-1) exactly
+          if (!md->is_cz) sincos_inl(th, s, c);
+          R rs = R(0);
+          if (pen_on) {
+            R val, slope;
+            penalty_eval(p.pen, th, val, slope);
+            reg_part += val;
+            rs = mul_rn(p.pen.r, slope);
+          }
+          cf[0] = c; cf[1] = s; cf[2] = rs;
+        }
+      }
+    }
+    __syncwarp();
+    if (it == p.nsteps) break;
+
+    // ---------------- forward sweep: Y = U V^dag ----------------
+    V yr[N], yi[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) { yr[r] = tv[2 * r]; yi[r] = tv[2 * r + 1]; }
+    SWP::forward(p, coef, yr, yi);
+
+    // ---------------- pivot to the Pauli basis ----------------
+    SWP::gather_wht(yr, yi);
+    const R tr = __shfl_sync(0xffffffffu, T::get(yr[0], 0), 0, TPS);
+    const R ti = __shfl_sync(0xffffffffu, T::get(yi[0], 0), 0, TPS);
+    R reg = sample_sum<TPS>(reg_part);
+    const R ab = sqrt_r(tr * tr + ti * ti);
+    const R loss = R(1) - mul_rn(ab, ab) / NN;
+    reg = mul_rn(p.pen.r, reg);
+
+    if (p.mode == M_LOSSGRAD) {
+      if (active && m == 0) {
+        p.loss_out[b] = loss;
+        if (p.reg_out) p.reg_out[b] = reg;
+      }
+      if (!p.grad_out) return;
+    } else {
+      const R regloss = add_rn(loss, reg);
+      bool improved;
+      if (gi == 0) {
+        improved = true;
+        if (active && m == 0) { p.init_regloss[b] = regloss; p.init_reg[b] = reg; }
+      } else {
+        improved = regloss < best;
+      }
+      // the parameters of an improving step are saved by the next update phase, which has them in registers
+      improved_prev = improved;
+      if (improved) { best = regloss; best_reg_v = reg; }
+      if (active && p.hist_regloss && m == 0 && gi < p.hist_len)
+        p.hist_regloss[b * p.hist_len + gi] = regloss;
+      if (active && p.hist_params && gi == 0)
+        for (int i = m; i < P; i += TPS) p.hist_params[b * p.hist_len * P + i] = ang[i];
+    }
+
+    // h[xr][z] = Re(i^{|x&z|} s W[x,z]),  s = i conj(t)/N^2 = (ti + i tr)/N^2,  x = (m << PB) | xr
+    V h[N];
+    {
+      const R sr = ti / NN, si = tr / NN;
+#pragma unroll
+      for (int z = 0; z < N; ++z) {
+        R hc[XR];
+#pragma unroll
+        for (int xr = 0; xr < XR; ++xr) {
+          const R wr = T::get(yr[z], xr), wi = T::get(yi[z], xr);
+          const R pq = sr * wr - si * wi, qq = sr * wi + si * wr;
+          const int k = __popc(m & (z >> PB)) + (PB ? (xr & z & 1) : 0);
+          const R val = (k & 1) ? -qq : pq;
+          hc[xr] = (k & 2) ? -val : val;
+        }
+        h[z] = T::make(hc[0], hc[XR - 1]);
+      }
+    }
+    // fused-gate coefficients (alpha, beta) -> SO(3) rows, in place (the forward sweep is done with them)
+    __syncwarp();
+    for (int g = m; g < p.n_su2; g += TPS) heis_su2_to_so3(coef + SW * g);
+    __syncwarp();
+
+    // ---------------- Heisenberg sweep ----------------
+    SWP::backward(p, coef, m, h);
+    __syncwarp();
+  }
+
+  if (p.mode == M_ADAM && active && m == 0) {
+    p.best_regloss[b] = best;
+    p.best_reg[b] = best_reg_v;
+  }
+}
+
+// ---- target packing for heis_kernel: Y0 = V^dag, lane l = column group, all rows per lane ----
+// dst index ((l * (N + 1) + r) * 2 + part) * CPT + k :  part 0 = Re, 1 = Im of conj(V[l*CPT + k][r])
+template <typename R>
+__global__ void pack_target_heis_kernel(const R* __restrict__ src, R* __restrict__ dst, int N, int cpt) {
+  const int total = (N / cpt) * (N + 1) * 2 * cpt;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int k = i % cpt, t = i / cpt;
+    int part = t % 2; t /= 2;
+    int r = t % (N + 1), l = t / (N + 1);
+    R val = R(0);
+    if (r < N) {
+      const R v = src[((size_t)(l * cpt + k) * N + r) * 2 + part];
+      val = part ? -v : v;
+    }
+    dst[i] = val;
+  }
+}
+
+// Launch geometry: spread the batch evenly over SMs and rounds so that the last wave is as full as the
+// first (every CTA runs all the Adam steps of its samples, so a ragged last wave costs a whole wave).
+//   ctas  resident CTAs per SM (independent instruction streams; default 2, env CPF_HEIS_CTAS)
+//   cap   samples per CTA allowed by shared memory, the thread limit and CPF_HEIS_WARPS
+struct HeisGeometry { int block, spb; long long grid; size_t smem; };
+inline HeisGeometry heis_geometry(long long B, size_t target_bytes, size_t per_sample, int tps, int maxt) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int ctas = 2, warps_max = maxt / 32;
+  if (const char* e = getenv("CPF_HEIS_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctas = v; }
+  if (const char* e = getenv("CPF_HEIS_WARPS")) { int v = atoi(e); if (v >= 1 && v <= warps_max) warps_max = v; }
+  const long long smem_cta = (long long)(227 * 1024) / ctas - 1024 - (long long)target_bytes - (long long)per_sample;
+  long long cap = smem_cta > 0 ? smem_cta / (long long)per_sample : 0;   // one spare slot for idle lanes
+  const long long cap_thr = (long long)warps_max * 32 / tps;
+  if (cap > cap_thr) cap = cap_thr;
+  if (cap < 1) cap = 1;
+  const long long slots = (long long)n_sm * ctas;
+  const long long rounds = (B + slots * cap - 1) / (slots * cap);
+  long long spb = (B + slots * rounds - 1) / (slots * rounds);
+  if (spb > cap) spb = cap;
+  if (spb < 1) spb = 1;
+  HeisGeometry g;
+  g.spb = (int)spb;
+  g.block = (int)((spb * tps + 31) / 32 * 32);
+  g.grid = (B + spb - 1) / spb;
+  g.smem = target_bytes + (size_t)(spb + 1) * per_sample;
+  return g;
+}
+
+template <typename R, int NQ, int CPT, typename SWP>
+int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
+  using C = HCfg<R, NQ, CPT>;
+  p.n_sched = 0; p.n_red = 0;
+  p.coef_stride = heis_coef_stride(p.n_su2, p.n_cp);
+  const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes, (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT);
+  p.spb = g.spb;
+  if (g.smem > 227 * 1024) {
+    err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
+    return CPF_ERR_UNSUPPORTED;
+  }
+  auto kern = heis_kernel<R, NQ, CPT, SWP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
+  if (g.grid <= 0) return CPF_OK;
+  if (g.grid > 2147483647LL) { err = "batch too large for one launch"; return CPF_ERR_UNSUPPORTED; }
+  kern<<<(unsigned)g.grid, g.block, g.smem, st>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { err = std::string("kernel launch: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
+  return CPF_OK;
+}
+
+// Returns true and sets `rc` when a Heisenberg kernel compiled for this layered program exists.
+// `dry` only answers the question (used before the target is staged in the heis layout).
+template <typename R> bool launch_heis(const KParams<R>& p, const Program& prog, cudaStream_t st,
+                                       std::string& err, int& rc, bool dry);
+// columns per thread of the heis kernels for (dtype, n): selects the target packing
+template <typename R> int heis_cpt(int n_qubits);
+template <typename R> int launch_pack_target_heis(const R* src, R* dst, int n_qubits, int cpt, cudaStream_t st);
+
+}  // namespace cpf

@@ -1,0 +1,186 @@
+"""Numpy model of the engine's Heisenberg-picture gradient (the math of csrc/heis_impl.cuh).
+
+HS loss L = 1 - |t|^2/N^2, t = Tr(V^dag U), U = G_M ... G_1.  With Y = U V^dag (forward sweep started
+from V^dag instead of the identity) t = Tr(Y), and for a gate G_k = exp(-i theta sigma/2):
+    dL/dtheta_k = Tr(H_k sigma),   H_k = Herm(s Z_k),  s = i conj(t)/N^2,
+    Z_k = G_k..G_1 V^dag G_M..G_{k+1},  Z_M = Y,  Z_{k-1} = G_k^dag Z_k G_k.
+H_k is Hermitian, so in the Pauli basis it is a REAL vector h[x, z] (x = bit-flip mask, z = sign mask):
+    h[x, z] = Re( i^{|x&z|} * s * W[x, z] ),  W[x, z] = sum_r (-1)^{|z&r|} Y[r, r^x]   (WHT over r)
+and every gate acts on h by a REAL linear map: a fused 1q gate rotates (h_X, h_Y, h_Z) of its qubit by
+the transpose of its SO(3) matrix, a CP gate rotates two "difference pairs" per (z1, z2) quad.
+The gradient sums are single entries of h: no reductions.
+
+This file is test infrastructure (tests/test_heisenberg_model.py checks it against the oracle)."""
+import math
+
+import numpy as np
+
+RX, RY, RZ, CP, CZ, CX = 0, 1, 2, 3, 4, 5
+SIG = {RX: np.array([[0, 1], [1, 0]], dtype=complex), RY: np.array([[0, -1j], [1j, 0]]),
+       RZ: np.array([[1, 0], [0, -1]], dtype=complex)}
+
+
+def popcount(v):
+    return bin(int(v)).count("1")
+
+
+def rot_mat(kind, a):
+    return math.cos(a / 2) * np.eye(2) - 1j * math.sin(a / 2) * SIG[kind]
+
+
+def so3_of(g):
+    """R[c, b] = Tr(sigma_c g sigma_b g^dag)/2  (g sigma_b g^dag = sum_c R[c,b] sigma_c)."""
+    s = [SIG[RX], SIG[RY], SIG[RZ]]
+    return np.array([[np.real(np.trace(s[c] @ g @ s[b] @ g.conj().T)) / 2 for b in range(3)] for c in range(3)])
+
+
+def apply_row(y, g, bit):
+    """y <- (g on row-index bit `bit`) y."""
+    N = y.shape[0]
+    idx = np.arange(N)
+    lo = idx[(idx >> bit) & 1 == 0]
+    hi = lo | (1 << bit)
+    a0, a1 = y[lo].copy(), y[hi].copy()
+    y[lo] = g[0, 0] * a0 + g[0, 1] * a1
+    y[hi] = g[1, 0] * a0 + g[1, 1] * a1
+
+
+def forward(n, ops, angles, target):
+    """Y = U V^dag, up to nothing (exact)."""
+    N = 1 << n
+    y = np.conj(np.asarray(target, dtype=complex)).T.copy()
+    idx = np.arange(N)
+    for kind, q0, q1, pi, const in ops:
+        a = angles[pi] if pi >= 0 else const
+        if kind in (RX, RY, RZ):
+            apply_row(y, rot_mat(kind, a), n - 1 - q0)
+        elif kind in (CP, CZ):
+            sel = ((idx >> (n - 1 - q0)) & 1 == 1) & ((idx >> (n - 1 - q1)) & 1 == 1)
+            y[sel] *= np.exp(1j * a) if kind == CP else -1.0
+        else:
+            raise ValueError("model covers rotations and diagonal two-qubit gates")
+    return y
+
+
+def wht_diagonals(y):
+    """W[x, z] = sum_r (-1)^{|z&r|} Y[r, r^x]: gather the x-diagonals, then a WHT over r."""
+    N = y.shape[0]
+    r = np.arange(N)
+    w = np.empty((N, N), dtype=complex)
+    for x in range(N):
+        a = y[r, r ^ x].copy()
+        h = 1
+        while h < N:                      # in-place butterflies, bit by bit
+            for i in range(N):
+                if i & h == 0:
+                    a[i], a[i | h] = a[i] + a[i | h], a[i] - a[i | h]
+            h <<= 1
+        w[x] = a
+    return w
+
+
+def to_pauli(y):
+    """Returns (t, h) with h[x, z] = Re(i^{|x&z|} s W[x,z]), s = i conj(t)/N^2."""
+    N = y.shape[0]
+    w = wht_diagonals(y)
+    t = w[0, 0]
+    s = 1j * np.conj(t) / N ** 2
+    h = np.empty((N, N))
+    for x in range(N):
+        for z in range(N):
+            h[x, z] = np.real((1j) ** (popcount(x & z) % 4) * s * w[x, z])
+    return t, h
+
+
+def conj_su2(h, m3, bit):
+    """h <- coefficients of G^dag H G for a 1q gate with (hX,hY,hZ)' = m3 @ (hX,hY,hZ), m3 = so3_of(G).T.
+    Components of qubit `bit`: X=(x=1,z=0), Y=(1,1), Z=(0,1), I=(0,0) untouched."""
+    N = h.shape[0]
+    b = 1 << bit
+    out = h.copy()
+    for x in range(N):
+        if x & b:
+            continue
+        for z in range(N):
+            if z & b:
+                continue
+            v = np.array([h[x | b, z], h[x | b, z | b], h[x, z | b]])
+            nv = m3 @ v
+            out[x | b, z], out[x | b, z | b], out[x, z | b] = nv
+    return out
+
+
+def conj_cp(h, a, bit1, bit2):
+    """h <- coefficients of CP^dag H CP.  Per (z1, z2) quad e[z1][z2] at fixed x and other z bits:
+      group A (x1=1,x2=0): pairs (e00,e01), (e10,e11)
+      group B (x1=0,x2=1): pairs (e00,e10), (e01,e11)
+      group C (x1=1,x2=1): pairs (e00,e11), (e01,e10) with the second pair SUMMED
+    v1 = (p0 - p1)/2, v2 = (p2 -/+ p3)/2 rotate by the CP angle."""
+    N = h.shape[0]
+    b1, b2 = 1 << bit1, 1 << bit2
+    c, s = math.cos(a), math.sin(a)
+    out = h.copy()
+    for x in range(N):
+        x1, x2 = (x & b1) != 0, (x & b2) != 0
+        if not (x1 or x2):
+            continue
+        for z in range(N):
+            if z & (b1 | b2):
+                continue
+            e = {(i, j): h[x, z | (b1 if i else 0) | (b2 if j else 0)] for i in (0, 1) for j in (0, 1)}
+            if x1 and not x2:
+                p = [(0, 0), (0, 1), (1, 0), (1, 1)]; sg = 1.0
+            elif x2 and not x1:
+                p = [(0, 0), (1, 0), (0, 1), (1, 1)]; sg = 1.0
+            else:
+                p = [(0, 0), (1, 1), (0, 1), (1, 0)]; sg = -1.0
+            v1 = (e[p[0]] - e[p[1]]) / 2
+            v2 = (e[p[2]] - sg * e[p[3]]) / 2
+            d1 = (c - 1) * v1 + SGN_CP * s * v2
+            d2 = (c - 1) * v2 - SGN_CP * s * v1
+            e[p[0]] += d1; e[p[1]] -= d1
+            e[p[2]] += d2; e[p[3]] -= sg * d2
+            for (i, j), val in e.items():
+                out[x, z | (b1 if i else 0) | (b2 if j else 0)] = val
+    return out
+
+
+SGN_CP = 1.0   # fixed by tests against brute force (see _selfcheck)
+
+
+def grad_hs(n, ops, angles, target):
+    """(loss, grad[P]) of the HS loss through the Heisenberg sweep."""
+    N = 1 << n
+    y = forward(n, ops, angles, target)
+    t, h = to_pauli(y)
+    loss = 1 - abs(t) ** 2 / N ** 2
+    grad = np.zeros(len(angles))
+    for kind, q0, q1, pi, const in reversed(ops):
+        a = angles[pi] if pi >= 0 else const
+        if kind in (RX, RY, RZ):
+            b = 1 << (n - 1 - q0)
+            if pi >= 0:
+                grad[pi] += {RX: h[b, 0], RY: h[b, b], RZ: h[0, b]}[kind]
+            h = conj_su2(h, so3_of(rot_mat(kind, a)).T, n - 1 - q0)
+        else:
+            b1, b2 = 1 << (n - 1 - q0), 1 << (n - 1 - q1)
+            if kind == CP and pi >= 0:
+                grad[pi] += -0.5 * (h[0, 0] - h[0, b1] - h[0, b2] + h[0, b1 | b2])
+            h = conj_cp(h, a if kind == CP else math.pi, n - 1 - q0, n - 1 - q1)
+    return loss, grad
+
+
+def pauli_brute(hm):
+    """h[x,z] = Re Tr(P_{x,z} Hm) by explicit Pauli strings (slow; for checks)."""
+    N = hm.shape[0]
+    n = N.bit_length() - 1
+    out = np.empty((N, N))
+    for x in range(N):
+        for z in range(N):
+            P = np.array([[1.0 + 0j]])
+            for bit in reversed(range(n)):       # most significant bit first in the kron
+                xb, zb = (x >> bit) & 1, (z >> bit) & 1
+                s = {(0, 0): np.eye(2), (1, 0): SIG[RX], (1, 1): SIG[RY], (0, 1): SIG[RZ]}[(xb, zb)]
+                P = np.kron(P, s)
+            out[x, z] = np.real(np.trace(P @ hm))
+    return out
