@@ -234,7 +234,7 @@ int run_loss_grad(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf
   p.mode = cpf::M_LOSSGRAD;
   p.angles = (R*)angles; p.loss_out = (R*)loss_out; p.reg_out = (R*)reg_out; p.grad_out = (R*)grad_out;
   uint8_t* cp_pen = nullptr; R* packed = nullptr; R* aux = nullptr;
-  const bool heis = use_heis<R>(prog, loss);
+  const bool heis = use_heis<R>(prog, loss) && (unsigned long long)batch * (unsigned long long)prog->n_params < (1ull << 32);
   rc = fill_penalty(prog, pen, p, &cp_pen, st);
   if (!rc) rc = heis ? stage_heis(prog, loss, p, &packed, &aux, st) : stage_target(prog, loss, p, single, &packed, st);
   if (!rc && grad_out) {
@@ -284,7 +284,7 @@ int run_adam(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf_pena
   p.best_reg = (R*)buf->best_reg; p.init_regloss = (R*)buf->init_regloss; p.init_reg = (R*)buf->init_reg;
   p.hist_params = (R*)buf->hist_params; p.hist_regloss = (R*)buf->hist_regloss; p.hist_len = buf->hist_len;
   uint8_t* cp_pen = nullptr; R* packed = nullptr; R* aux = nullptr;
-  const bool heis = use_heis<R>(prog, loss);
+  const bool heis = use_heis<R>(prog, loss) && (unsigned long long)batch * (unsigned long long)prog->n_params < (1ull << 32);
   rc = fill_penalty(prog, pen, p, &cp_pen, st);
   if (!rc) rc = heis ? stage_heis(prog, loss, p, &packed, &aux, st) : stage_target(prog, loss, p, single, &packed, st);
   std::string err;

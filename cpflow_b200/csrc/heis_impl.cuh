@@ -48,8 +48,8 @@ struct HCfg {
   static constexpr int PB = CPT == 2 ? 1 : 0;   // x bits of a thread held in registers
   static constexpr int XR = 1 << PB;
   static constexpr int TPS = N / CPT;           // threads per sample
-  // forward state registers: 2 * N * CPT words (x2 for double) -> register cap 128 (512 threads) or 255
-  static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? 512 : 256;
+  // forward state registers: 2 * N * CPT words (x2 for double) -> register cap 168 (384 threads) or 255
+  static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? 384 : 256;
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
 };
 
@@ -319,20 +319,24 @@ __device__ __forceinline__ void heis_su2_to_so3(R* cf) {
 // ------------------------------------------------------------------------------------------
 // update / coefficient phase helpers (per gate, executed by the gate's owner thread)
 // ------------------------------------------------------------------------------------------
+// Per-sample arrays are addressed as array[off + index] with a 32-bit element offset off = b * P (the
+// host checks B * P < 2^32): one IMAD.WIDE per access instead of a 64-bit multiply chain.
 template <typename R>
 struct UpdCtx {
   int phase;            // PH_COEF / PH_ADAM / PH_GRAD
   bool active;          // this thread's sample exists
   bool store_best;      // the step being finished improved on the best regloss: keep its parameters
   bool skip_coef;       // last pass: no new coefficients
-  long long b, gu;      // sample, step being finished
+  bool first;           // step 0: the Adam moments start from zero (not read)
+  bool hist;            // parameter history is recorded for this step
+  unsigned off;         // b * P
+  size_t hist_off;      // (b * hist_len + gu + 1) * P
   R bc1, bc2, ibc1, ibc2;
-  R* ang; R* mom; R* vel; const uint8_t* frz;
 };
 
+static __device__ __noinline__ SinCos<float> sincos_slow_v(float x) { float s, c; sincosf(x, &s, &c); return {s, c}; }
 // sin/cos for the parameter phase, inlined so the three evaluations of a fused gate interleave
 __device__ __forceinline__ void sincos_inl(float x, float& s, float& c) {
-  if (fabsf(x) > 48000.f) { sincos_slow_f(x, &s, &c); return; }
   const float j = rintf(x * 0.636619747f);
   float r = fmaf(j, -1.57079601e+00f, x);
   r = fmaf(j, -3.13916473e-07f, r);
@@ -349,6 +353,7 @@ __device__ __forceinline__ void sincos_inl(float x, float& s, float& c) {
   const float cc = (q & 1) ? sp : cp;
   s = (q & 2) ? -ss : ss;
   c = ((q + 1) & 2) ? -cc : cc;
+  if (fabsf(x) > 48000.f) { const SinCos<float> t = sincos_slow_v(x); s = t.s; c = t.c; }
 }
 __device__ __forceinline__ void sincos_inl(double x, double& s, double& c) { sincos_r(x, s, c); }
 
@@ -375,71 +380,100 @@ __device__ __forceinline__ void adam_inl(const KParams<float>& p, const UpdCtx<f
 // one parameter: gradient sink (loss_grad mode) or best-parameter bookkeeping + Adam step
 template <typename R>
 __device__ __forceinline__ void heis_apply(const KParams<R>& p, const UpdCtx<R>& u, int pi, R g, R& th, R mu, R nu) {
-  const int P = p.P;
+  const unsigned idx = u.off + (unsigned)pi;
   if (u.phase == PH_GRAD) {
-    if (u.active) p.grad_out[u.b * P + pi] = g;
+    if (u.active) p.grad_out[idx] = g;
     return;
   }
   // th is still the pre-update parameter of the step being finished (optimization.py:70-73)
-  if (u.store_best && u.active) p.best_params[u.b * P + pi] = th;
-  if (u.frz && u.frz[pi]) return;
+  if (u.store_best && u.active) p.best_params[idx] = th;
+  if (p.freeze && p.freeze[idx]) return;
   adam_inl(p, u, g, th, mu, nu);
   if (u.active) {
-    u.mom[pi] = mu; u.vel[pi] = nu; u.ang[pi] = th;
-    if (p.hist_params && u.gu + 1 < p.hist_len)
-      p.hist_params[(u.b * p.hist_len + u.gu + 1) * P + pi] = th;
+    p.m[idx] = mu; p.v[idx] = nu; p.angles[idx] = th;
+    if (u.hist) p.hist_params[u.hist_off + pi] = th;
   }
+}
+
+// (alpha, beta) <- R_a(c, s) * (alpha, beta) for a rotation about a compile-time-foldable axis: 8 FMA
+template <typename R>
+__device__ __forceinline__ void su2_lmul_axis(int a, R c, R s, R& ar, R& ai, R& br, R& bi) {
+  if (a == 0) {        // Rx = [[c, -is], [-is, c]]
+    const R nar = c * ar + s * bi, nai = c * ai - s * br, nbr = c * br + s * ai, nbi = c * bi - s * ar;
+    ar = nar; ai = nai; br = nbr; bi = nbi;
+  } else if (a == 1) { // Ry = [[c, -s], [s, c]]
+    const R nar = c * ar - s * br, nai = c * ai - s * bi, nbr = c * br + s * ar, nbi = c * bi + s * ai;
+    ar = nar; ai = nai; br = nbr; bi = nbi;
+  } else if (a == 2) { // Rz = diag(c - is, c + is)
+    const R nar = c * ar + s * ai, nai = c * ai - s * ar, nbr = c * br - s * bi, nbi = c * bi + s * br;
+    ar = nar; ai = nai; br = nbr; bi = nbi;
+  }
+}
+
+// Everything the update of one fused gate reads from global / shared memory.  The gate loops below are
+// software pipelined: the loads of the next gate are issued before the current gate is processed, so the
+// L2 round trips (theta, Adam moments, half-angle cos/sin of the fused rotations) overlap the arithmetic.
+template <typename R>
+struct GateIn {
+  int pi0, pi1, pi2;
+  R th0, th1, th2, mu0, nu0, mu1, nu1, mu2, nu2, sx, sy, sz, c2, s2, c3, s3;
+};
+template <typename R>
+__device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const UpdCtx<R>& u, bool valid,
+                                                    const Su2Meta* md, const R* cf, const R* ax) {
+  GateIn<R> in;
+  in.pi0 = in.pi1 = in.pi2 = -1;
+  in.th0 = in.th1 = in.th2 = in.mu0 = in.nu0 = in.mu1 = in.nu1 = in.mu2 = in.nu2 = R(0);
+  in.sx = in.sy = in.sz = in.c2 = in.s2 = in.c3 = in.s3 = R(0);
+  if (!valid) return in;
+  in.pi0 = md->pidx[0]; in.pi1 = md->pidx[1]; in.pi2 = md->pidx[2];
+  if (in.pi0 >= 0) in.th0 = p.angles[u.off + (unsigned)in.pi0]; else in.th0 = R(md->cangle[0]);
+  if (in.pi1 >= 0) in.th1 = p.angles[u.off + (unsigned)in.pi1]; else in.th1 = R(md->cangle[1]);
+  if (in.pi2 >= 0) in.th2 = p.angles[u.off + (unsigned)in.pi2]; else in.th2 = R(md->cangle[2]);
+  if (u.phase != PH_COEF) {
+    if (u.phase == PH_ADAM && !u.first) {
+      if (in.pi0 >= 0) { in.mu0 = p.m[u.off + (unsigned)in.pi0]; in.nu0 = p.v[u.off + (unsigned)in.pi0]; }
+      if (in.pi1 >= 0) { in.mu1 = p.m[u.off + (unsigned)in.pi1]; in.nu1 = p.v[u.off + (unsigned)in.pi1]; }
+      if (in.pi2 >= 0) { in.mu2 = p.m[u.off + (unsigned)in.pi2]; in.nu2 = p.v[u.off + (unsigned)in.pi2]; }
+    }
+    in.sx = cf[3]; in.sy = cf[7]; in.sz = cf[11];
+    Vec4Load<R>::ld(ax, in.c2, in.s2, in.c3, in.s3);
+  }
+  return in;
 }
 
 // Fused one-qubit gate: finish the step (chain rule through the fusion, Adam), then the new (alpha, beta).
 // AX* >= 0: compile-time rotation axes (the selects fold away); AX0 == -2: axes from the gate metadata.
 template <typename R, int AX0, int AX1, int AX2>
 __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, const Su2Meta* md,
-                                                R* cf, R* ax) {
+                                                GateIn<R> in, R* cf, R* ax) {
   const int ax0 = AX0 == -2 ? md->axis[0] : AX0;
   const int ax1 = AX0 == -2 ? md->axis[1] : AX1;
   const int ax2 = AX0 == -2 ? md->axis[2] : AX2;
-  const int pi0 = md->pidx[0], pi1 = md->pidx[1], pi2 = md->pidx[2];
-  R th0, th1, th2;
-  if (pi0 >= 0) th0 = u.ang[pi0]; else th0 = R(md->cangle[0]);
-  if (pi1 >= 0) th1 = u.ang[pi1]; else th1 = R(md->cangle[1]);
-  if (pi2 >= 0) th2 = u.ang[pi2]; else th2 = R(md->cangle[2]);
   if (u.phase != PH_COEF) {
-    // all loads of the gate first: the three Adam updates then run back to back
-    R mu0 = R(0), nu0 = R(0), mu1 = R(0), nu1 = R(0), mu2 = R(0), nu2 = R(0);
-    if (u.phase == PH_ADAM && u.gu > 0) {
-      if (pi0 >= 0) { mu0 = u.mom[pi0]; nu0 = u.vel[pi0]; }
-      if (pi1 >= 0) { mu1 = u.mom[pi1]; nu1 = u.vel[pi1]; }
-      if (pi2 >= 0) { mu2 = u.mom[pi2]; nu2 = u.vel[pi2]; }
-    }
-    const R sx = cf[3], sy = cf[7], sz = cf[11];
-    R c2, s2, c3, s3;
-    Vec4Load<R>::ld(ax, c2, s2, c3, s3);
-    const R C2 = c2 * c2 - s2 * s2, S2 = R(2) * c2 * s2;
-    const R C3 = c3 * c3 - s3 * s3, S3 = R(2) * c3 * s3;
+    const R C2 = in.c2 * in.c2 - in.s2 * in.s2, S2 = R(2) * in.c2 * in.s2;
+    const R C3 = in.c3 * in.c3 - in.s3 * in.s3, S3 = R(2) * in.c3 * in.s3;
     R x1 = ax1 == 0, y1 = ax1 == 1, z1 = ax1 == 2;
     rot_axis(ax2, C3, S3, x1, y1, z1);
     R x0 = ax0 == 0, y0 = ax0 == 1, z0 = ax0 == 2;
     rot_axis(ax1, C2, S2, x0, y0, z0);
     rot_axis(ax2, C3, S3, x0, y0, z0);
-    const R g2 = sel3(ax2, sx, sy, sz);
-    const R g1 = x1 * sx + y1 * sy + z1 * sz;
-    const R g0 = x0 * sx + y0 * sy + z0 * sz;
-    if (pi2 >= 0) heis_apply(p, u, pi2, g2, th2, mu2, nu2);
-    if (pi1 >= 0) heis_apply(p, u, pi1, g1, th1, mu1, nu1);
-    if (pi0 >= 0) heis_apply(p, u, pi0, g0, th0, mu0, nu0);
+    const R g2 = sel3(ax2, in.sx, in.sy, in.sz);
+    const R g1 = x1 * in.sx + y1 * in.sy + z1 * in.sz;
+    const R g0 = x0 * in.sx + y0 * in.sy + z0 * in.sz;
+    if (in.pi2 >= 0) heis_apply(p, u, in.pi2, g2, in.th2, in.mu2, in.nu2);
+    if (in.pi1 >= 0) heis_apply(p, u, in.pi1, g1, in.th1, in.mu1, in.nu1);
+    if (in.pi0 >= 0) heis_apply(p, u, in.pi0, g0, in.th0, in.mu0, in.nu0);
   }
   if (!u.skip_coef) {
     R c0 = R(1), s0 = R(0), c1 = R(1), s1 = R(0), c2 = R(1), s2 = R(0);
-    if (ax0 >= 0) sincos_inl(th0 * R(0.5), s0, c0);
-    if (ax1 >= 0) sincos_inl(th1 * R(0.5), s1, c1);
-    if (ax2 >= 0) sincos_inl(th2 * R(0.5), s2, c2);
-    R ar, ai, br, bi, a2r, a2i, b2r, b2i;
+    if (ax0 >= 0) sincos_inl(in.th0 * R(0.5), s0, c0);
+    if (ax1 >= 0) sincos_inl(in.th1 * R(0.5), s1, c1);
+    if (ax2 >= 0) sincos_inl(in.th2 * R(0.5), s2, c2);
+    R ar, ai, br, bi;
     su2_of(ax0, c0, s0, ar, ai, br, bi);
-    su2_of(ax1, c1, s1, a2r, a2i, b2r, b2i);
-    su2_mul(a2r, a2i, b2r, b2i, ar, ai, br, bi);
-    su2_of(ax2, c2, s2, a2r, a2i, b2r, b2i);
-    su2_mul(a2r, a2i, b2r, b2i, ar, ai, br, bi);
+    su2_lmul_axis(ax1, c1, s1, ar, ai, br, bi);
+    su2_lmul_axis(ax2, c2, s2, ar, ai, br, bi);
     cf[0] = ar; cf[1] = ai; cf[2] = br; cf[3] = bi;
     if (u.active) { ax[0] = c1; ax[1] = s1; ax[2] = c2; ax[3] = s2; }
   }
@@ -448,13 +482,28 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
 constexpr int AXP_ZXZ = 2 | (0 << 4) | (2 << 8);
 constexpr int AXP_XYZ = 0 | (1 << 4) | (2 << 8);
 constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
+
+// gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined
+template <typename R, int AX0, int AX1, int AX2>
+__device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const UpdCtx<R>& u, int g0, int g_end, int stride,
+                                              R* coef, R* aux) {
+  constexpr int SW = HEIS_SU2_WORDS;
+  GateIn<R> cur = heis_gate_load(p, u, g0 < g_end, p.su2 + g0, coef + SW * g0, aux + 4 * g0);
+#pragma unroll 1
+  for (int g = g0; g < g_end; g += stride) {
+    const int gn = g + stride;
+    const GateIn<R> nxt = heis_gate_load(p, u, gn < g_end, p.su2 + gn, coef + SW * gn, aux + 4 * gn);
+    heis_su2_update<R, AX0, AX1, AX2>(p, u, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
+    cur = nxt;
+  }
+}
 template <typename R>
-__device__ __forceinline__ void heis_su2_update_any(int axp, const KParams<R>& p, const UpdCtx<R>& u,
-                                                    const Su2Meta* md, R* cf, R* ax) {
-  if (axp == AXP_XYZ) heis_su2_update<R, 0, 1, 2>(p, u, md, cf, ax);
-  else if (axp == AXP_ZXZ) heis_su2_update<R, 2, 0, 2>(p, u, md, cf, ax);
-  else if (axp == AXP_XZ) heis_su2_update<R, 0, 2, -1>(p, u, md, cf, ax);
-  else heis_su2_update<R, -2, -2, -2>(p, u, md, cf, ax);
+__device__ __forceinline__ void heis_su2_loop_any(int axp, const KParams<R>& p, const UpdCtx<R>& u, int g0, int g_end,
+                                                  int stride, R* coef, R* aux) {
+  if (axp == AXP_XYZ) heis_su2_loop<R, 0, 1, 2>(p, u, g0, g_end, stride, coef, aux);
+  else if (axp == AXP_ZXZ) heis_su2_loop<R, 2, 0, 2>(p, u, g0, g_end, stride, coef, aux);
+  else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1>(p, u, g0, g_end, stride, coef, aux);
+  else heis_su2_loop<R, -2, -2, -2>(p, u, g0, g_end, stride, coef, aux);
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -498,11 +547,8 @@ heis_kernel(const KParams<R> p) {
   R* coef_cp = coef + SW * p.n_su2;
   const V* tv = reinterpret_cast<const V*>(s_target) + 2 * (size_t)m * (N + 1);
 
-  R* ang = p.angles + b * P;
-  R* mom = p.m ? p.m + b * P : nullptr;
-  R* vel = p.v ? p.v + b * P : nullptr;
-  R* aux = p.aux + b * (long long)p.n_su2 * 4;
-  const uint8_t* frz = p.freeze ? p.freeze + b * P : nullptr;
+  const unsigned off = (unsigned)(b * P);   // host: B * P < 2^32
+  R* aux = p.aux + (size_t)b * p.n_su2 * 4;
   const R NN = R(N) * R(N);
 
   R best = R(0), best_reg_v = R(0);
@@ -516,21 +562,22 @@ heis_kernel(const KParams<R> p) {
     R reg_part = R(0);
     {
       UpdCtx<R> u;
-      u.phase = phase; u.active = active; u.b = b; u.gu = gi - 1;
+      u.phase = phase; u.active = active; u.off = off;
+      const long long gu = gi - 1;
+      u.first = gu == 0;
       u.store_best = improved_prev && p.mode == M_ADAM && phase == PH_ADAM;
       u.skip_coef = it == p.nsteps;
-      u.ang = ang; u.mom = mom; u.vel = vel; u.frz = frz;
+      u.hist = p.hist_params != nullptr && gu + 1 < p.hist_len;
+      u.hist_off = u.hist ? (size_t)(b * p.hist_len + gu + 1) * (size_t)P : 0;
       u.bc1 = u.bc2 = u.ibc1 = u.ibc2 = R(1);
       if (phase == PH_ADAM) {
-        u.bc1 = bias_corr(p.b1, R(u.gu + 1));
-        u.bc2 = bias_corr(p.b2, R(u.gu + 1));
+        u.bc1 = bias_corr(p.b1, R(gu + 1));
+        u.bc2 = bias_corr(p.b2, R(gu + 1));
         u.ibc1 = R(1) / u.bc1; u.ibc2 = R(1) / u.bc2;
       }
       // surface gates (slots < NQ) and block gates (the rest) each share one axis pattern in the templates
-      for (int g = m; g < NQ && g < p.n_su2; g += TPS)
-        heis_su2_update_any(p.axp_surface, p, u, p.su2 + g, coef + SW * g, aux + 4 * g);
-      for (int g = NQ + m; g < p.n_su2; g += TPS)
-        heis_su2_update_any(p.axp_block, p, u, p.su2 + g, coef + SW * g, aux + 4 * g);
+      heis_su2_loop_any(p.axp_surface, p, u, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any(p.axp_block, p, u, NQ + m, p.n_su2, TPS, coef, aux);
       for (int k = m; k < p.n_cp; k += TPS) {
         const CpMeta* md = p.cp + k;
         R* cf = coef_cp + CW * k;
@@ -538,10 +585,10 @@ heis_kernel(const KParams<R> p) {
         const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
                             (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
         R th;
-        if (pi >= 0) th = ang[pi]; else th = R(md->cangle);
+        if (pi >= 0) th = p.angles[off + (unsigned)pi]; else th = R(md->cangle);
         if (phase != PH_COEF && pi >= 0) {
           R mu = R(0), nu = R(0);
-          if (phase == PH_ADAM && u.gu > 0) { mu = mom[pi]; nu = vel[pi]; }
+          if (phase == PH_ADAM && !u.first) { mu = p.m[off + (unsigned)pi]; nu = p.v[off + (unsigned)pi]; }
           // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
           heis_apply(p, u, pi, add_rn(cf[0], cf[2]), th, mu, nu);
         }
@@ -598,7 +645,7 @@ heis_kernel(const KParams<R> p) {
       if (active && p.hist_regloss && m == 0 && gi < p.hist_len)
         p.hist_regloss[b * p.hist_len + gi] = regloss;
       if (active && p.hist_params && gi == 0)
-        for (int i = m; i < P; i += TPS) p.hist_params[b * p.hist_len * P + i] = ang[i];
+        for (int i = m; i < P; i += TPS) p.hist_params[b * p.hist_len * P + i] = p.angles[off + i];
     }
 
     // h[xr][z] = Re(i^{|x&z|} s W[x,z]),  s = i conj(t)/N^2 = (ti + i tr)/N^2,  x = (m << PB) | xr

@@ -369,3 +369,77 @@ def test_layered_and_interpreter_kernels_agree():
             tol = 1e-12 if dt == torch.float64 else 2e-5
             for x, y in zip(*outs):
                 assert float((x - y).abs().max()) <= tol * max(1.0, float(y.abs().max()))
+
+
+def _with_env(env, fn):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_three_engines_agree():
+    """HS loss on layered templates runs on the Heisenberg-picture kernel (heis_impl.cuh); the
+    state-adjoint LayerSweep kernel (CPF_ENGINE=adjoint) and the interpreter (CPF_NO_LAYERED=1) must give
+    the same loss, gradient and Adam trajectory, also for CZ templates and constrained programs."""
+    cases = [(4, chain_layer(4), 40, "xyz", "cp"), (4, [[0, 1], [0, 2], [0, 3]], 11, "xz", "cp"),
+             (3, connected_layer(3), 7, "xyz", "cp"), (5, chain_layer(5), 9, "xyz", "cp"),
+             (4, connected_layer(4), 14, "zyx", "cp"), (3, chain_layer(3), 6, "xyz", "cz"), (2, [[0, 1]], 4, "xyz", "cp")]
+    for n, layer, K, rg, ent in cases:
+        anz = Ansatz(n, ent, fill_layers(layer, K), rg)
+        V = unitary_group.rvs(2 ** n, random_state=4)
+        for dt in (torch.float32, torch.float64):
+            a = torch.tensor(np.random.default_rng(K).uniform(0, 6.28, (37, anz.num_angles)), dtype=dt, device=DEV)
+            progs = [anz.program]
+            if ent == "cp":   # constrained program: some CP angles projected to 0 / pi and frozen
+                idx = [i for i in range(anz.num_angles) if anz.cp_mask[i]][::2]
+                progs.append(anz.constrained([math.pi if j % 2 else 0.0 for j in range(len(idx))], idx)[0])
+
+            def run(prog):
+                aa = a[:, :prog.n_params].contiguous()
+                p_ = pen() if prog is anz.program and ent == "cp" else None
+                lo, rg_, gr = prog.loss_grad(aa, Loss("hs", V), p_)
+                st = prog.adam_state(aa.clone())
+                prog.adam_run(st, Loss("hs", V), p_, 0.1, 9)
+                return lo.clone(), gr.clone(), st.best_regloss.clone(), st.angles.clone(), st.best_params.clone()
+
+            for prog in progs:
+                ref = _with_env({"CPF_NO_LAYERED": "1"}, lambda: run(prog))
+                adj = _with_env({"CPF_ENGINE": "adjoint"}, lambda: run(prog))
+                heis = run(prog)
+                tol = 1e-12 if dt == torch.float64 else 3e-5
+                for x, y, z in zip(ref, adj, heis):
+                    sc = max(1.0, float(x.abs().max()))
+                    assert float((x - y).abs().max()) <= tol * sc
+                    assert float((x - z).abs().max()) <= tol * sc, (n, K, rg, ent, dt)
+
+
+def test_heis_launch_geometry_edge_cases():
+    """Batch sizes around the CTA / wave boundaries and every CTAs-per-SM setting give per-sample results that
+    do not depend on the launch geometry (idle sample slots, spare coefficient store, ragged last CTA)."""
+    anz = Ansatz(4, "cp", fill_layers(chain_layer(4), 12))
+    V = unitary_group.rvs(16, random_state=1)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    a_all = anz.program.initial_angles(3, 4 * n_sm + 50).double()
+    lo_ref, _, gr_ref = anz.program.loss_grad(a_all, Loss("hs", V), pen())
+    st_ref = anz.program.adam_state(a_all.clone())
+    anz.program.adam_run(st_ref, Loss("hs", V), pen(), 0.1, 5)
+    for B in (1, 2, 3, 5, n_sm - 1, n_sm, n_sm + 1, 2 * n_sm + 1, 4 * n_sm + 50):
+        for env in ({}, {"CPF_HEIS_CTAS": "1"}, {"CPF_HEIS_CTAS": "4", "CPF_HEIS_WARPS": "1"}):
+            def run():
+                a = a_all[:B].contiguous()
+                lo, _, gr = anz.program.loss_grad(a, Loss("hs", V), pen())
+                st = anz.program.adam_state(a.clone())
+                anz.program.adam_run(st, Loss("hs", V), pen(), 0.1, 5)
+                return lo, gr, st
+            lo, gr, st = _with_env(env, run)
+            assert torch.equal(lo, lo_ref[:B]) and torch.equal(gr, gr_ref[:B]), (B, env)
+            assert torch.equal(st.angles, st_ref.angles[:B]) and torch.equal(st.best_params, st_ref.best_params[:B])
+            assert torch.equal(st.best_regloss, st_ref.best_regloss[:B])

@@ -1,0 +1,88 @@
+"""The math of the Heisenberg-picture kernel (csrc/heis_impl.cuh), restated in numpy by
+tools/heisenberg_model.py, against the oracle: Pauli-basis pivot, SO(3) and CP maps, and the full
+loss + gradient of the HS loss (matrix_utils.py:35-42) for CP / CZ templates.  CPU only."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+from scipy.stats import unitary_group
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import heisenberg_model as H  # noqa: E402
+from oracle import cpflow_oracle as O  # noqa: E402
+
+
+def _embed(g, bit, n):
+    G = np.array([[1.0 + 0j]])
+    for b in reversed(range(n)):
+        G = np.kron(G, g if b == bit else np.eye(2))
+    return G
+
+
+def test_pivot_and_gate_maps_against_brute_force():
+    rng = np.random.default_rng(1)
+    n, N = 3, 8
+    y = rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))
+    t, h = H.to_pauli(y)
+    A = 1j * np.conj(t) / N ** 2 * y
+    Hm = (A + A.conj().T) / 2
+    hb = H.pauli_brute(Hm)
+    assert np.abs(h - hb).max() < 1e-14
+    g = H.rot_mat(H.RZ, 0.7) @ H.rot_mat(H.RY, -1.1) @ H.rot_mat(H.RX, 2.2)
+    for bit in range(n):
+        G = _embed(g, bit, n)
+        assert np.abs(H.conj_su2(hb, H.so3_of(g).T, bit) - H.pauli_brute(G.conj().T @ Hm @ G)).max() < 1e-14
+    idx = np.arange(N)
+    for b1, b2 in [(0, 1), (1, 0), (0, 2), (2, 1)]:
+        for a in (0.83, math.pi, -2.1):
+            d = np.ones(N, dtype=complex)
+            d[((idx >> b1) & 1 == 1) & ((idx >> b2) & 1 == 1)] = np.exp(1j * a)
+            Cm = np.diag(d)
+            assert np.abs(H.conj_cp(hb, a, b1, b2) - H.pauli_brute(Cm.conj().T @ Hm @ Cm)).max() < 1e-14
+
+
+def test_so3_from_quaternion_formula():
+    """heis_su2_to_so3: w = Re alpha, z = -Im alpha, y = Re beta, x = -Im beta."""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        g = H.rot_mat(H.RZ, rng.uniform(-7, 7)) @ H.rot_mat(H.RY, rng.uniform(-7, 7)) @ H.rot_mat(H.RX, rng.uniform(-7, 7))
+        al, be = g[0, 0], g[1, 0]
+        w, z, y, x = al.real, -al.imag, be.real, -be.imag
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        assert np.abs(R - H.so3_of(g)).max() < 1e-14
+
+
+@pytest.mark.parametrize("n,layer,K,rg,ent", [(3, O.chain_layer(3), 5, "xyz", "cp"), (4, O.chain_layer(4), 7, "xyz", "cp"),
+                                              (4, [[0, 1], [0, 2], [0, 3]], 4, "xz", "cp"),
+                                              (3, O.connected_layer(3), 6, "zyx", "cp"), (2, [[0, 1]], 3, "xyz", "cp")])
+def test_heisenberg_gradient_equals_oracle(n, layer, K, rg, ent):
+    rng = np.random.default_rng(K)
+    anz = O.cp_ansatz(layer, K, rg)
+    ops = O.ansatz_program(anz)
+    tgt = unitary_group.rvs(1 << n, random_state=3)
+    a = rng.uniform(0, 2 * np.pi, anz.num_angles)
+    l, g = H.grad_hs(n, ops, a, tgt)
+    ol, _, og = O.loss_and_grad_batched(n, ops, torch.tensor(a)[None], "hs", torch.tensor(tgt))
+    assert abs(l - float(ol[0])) < 1e-13
+    assert np.abs(g - og[0].numpy()).max() < 1e-13
+    l2, g2 = O.hand_adjoint_grad(n, ops, a, "hs", tgt)
+    assert abs(l - l2) < 1e-13 and np.abs(g - g2).max() < 1e-13
+
+
+def test_heisenberg_gradient_with_cz_and_constants():
+    """CZ entanglers (is_cz) and constant angles (projected / frozen CP gates, cp_utils.py:70-108)."""
+    n = 3
+    ops = [(H.RZ, 0, -1, 0, 0.0), (H.RX, 1, -1, 1, 0.0), (H.CZ, 0, 1, -1, 0.0), (H.RY, 0, -1, 2, 0.0),
+           (H.CP, 1, 2, -1, math.pi), (H.RX, 2, -1, 3, 0.0), (H.CP, 0, 2, 4, 0.0), (H.RZ, 1, -1, -1, 0.37),
+           (H.RY, 2, -1, 5, 0.0)]
+    a = np.random.default_rng(0).uniform(0, 6.28, 6)
+    tgt = unitary_group.rvs(8, random_state=5)
+    l, g = H.grad_hs(n, ops, a, tgt)
+    l2, g2 = O.hand_adjoint_grad(n, ops, a, "hs", tgt)
+    assert abs(l - l2) < 1e-13 and np.abs(g - g2).max() < 1e-13
