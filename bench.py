@@ -15,8 +15,9 @@ batch fixed); timing is CUDA events on the launching stream, max over ranks.
 Keys beyond the base contract:
   roofline     FP32 CUDA-core roofline of the engine kernel (the path is gate
                arithmetic, not HBM or tensor-core bound).  achieved = algorithmic flops per launch
-               (C*N*(16*G1+4*K+8) per eval, uncompute not credited) / mean launch time measured
-               live with CUDA events; peak = FP32 FMA issue peak measured live by tools/fp32_peak
+               (C*N*(16*G1+4*K+8) per eval, the adjoint-sweep count; uncompute not credited) / mean
+               launch time measured live with CUDA events.  The Heisenberg-picture kernel
+               (csrc/heis_impl.cuh) needs fewer executed flops than that count; peak = FP32 FMA issue peak measured live by tools/fp32_peak
                on the same GPU (MEASURED_PEAKS.json carries no FP32 figure).  The HBM side is
                reported next to it (hbm_*), it is not the bound.
   cpu_baseline the CPU oracle (torch restatement of the reference's JAX loop; JAX is not in the
@@ -338,7 +339,11 @@ def run_b200(args):
             traffic = json.load(open(rp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp32", "kernel": "cpf::engine_kernel<float,4,2,2,false>",
+    roofline = {"bound": "fp32", "kernel": "cpf::heis_kernel<float,4,2,HeisSweep<chain>>",
+                "note": "FP32 CUDA-core bound (north_star: no tensor cores, not HBM). 'achieved' credits the adjoint-"
+                        "sweep flop count of SURVEY.md 8(d); the Heisenberg-picture kernel executes ~0.6 M flop per "
+                        "eval (real Pauli-basis backward sweep), so frac can exceed the FMA-pipe utilisation ncu "
+                        "reports (profiles/).",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": peak_src, "flops_per_eval": flops_eval, "evals_per_launch": B * T,
                 "launch_ms_mean": launch_mean, "traffic": traffic,

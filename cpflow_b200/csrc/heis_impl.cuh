@@ -702,14 +702,14 @@ __global__ void pack_target_heis_kernel(const R* __restrict__ src, R* __restrict
 
 // Launch geometry: spread the batch evenly over SMs and rounds so that the last wave is as full as the
 // first (every CTA runs all the Adam steps of its samples, so a ragged last wave costs a whole wave).
-//   ctas  resident CTAs per SM (independent instruction streams; default 2, env CPF_HEIS_CTAS)
+//   ctas  resident CTAs per SM (independent instruction streams; default 1: one synchronised stream shares the instruction cache; env CPF_HEIS_CTAS)
 //   cap   samples per CTA allowed by shared memory, the thread limit and CPF_HEIS_WARPS
 struct HeisGeometry { int block, spb; long long grid; size_t smem; };
 inline HeisGeometry heis_geometry(long long B, size_t target_bytes, size_t per_sample, int tps, int maxt) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  int ctas = 2, warps_max = maxt / 32;
+  int ctas = 1, warps_max = maxt / 32;
   if (const char* e = getenv("CPF_HEIS_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctas = v; }
   if (const char* e = getenv("CPF_HEIS_WARPS")) { int v = atoi(e); if (v >= 1 && v <= warps_max) warps_max = v; }
   const long long smem_cta = (long long)(227 * 1024) / ctas - 1024 - (long long)target_bytes - (long long)per_sample;
