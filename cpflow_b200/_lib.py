@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcpflow_b200.so")
 
 MAX_SEGMENTS = 16
-MAX_QUBITS = 5
+MAX_QUBITS = 7
 
 # enums (mirror include/cpflow_b200.h)
 RX, RY, RZ, CP, CZ, CX = 0, 1, 2, 3, 4, 5

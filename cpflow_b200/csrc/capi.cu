@@ -53,7 +53,9 @@ int device_program(const cpf::Program* prog, cpf::DeviceProgram* out) {
 
 // decoded schedule for a kernel configuration with `rb` register bits, cached per device
 int device_decoded(const cpf::Program* prog, int rb, cpf::DeviceDecoded* out) {
-  if (rb < 0 || rb >= 8) return fail(CPF_ERR_UNSUPPORTED, "unsupported number of qubits");
+  if (rb < 0 || rb >= 8)
+    return fail(CPF_ERR_UNSUPPORTED, "full-unitary losses need n <= 5 qubits (6-7 qubits: state preparation and "
+                                     "cpf_unitary only)");
   int dev = 0;
   CPF_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(prog->mu);
@@ -199,6 +201,7 @@ int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams
     }
     return pat < 0 ? 0xffff : pat;
   };
+  for (int q = 0; q < 8; ++q) p.last_slot[q] = q < prog->n_qubits ? prog->last_slot[q] : 0;
   p.axp_surface = pattern(0, (size_t)prog->n_qubits);
   p.axp_block = pattern((size_t)prog->n_qubits, prog->su2.size());
   return CPF_OK;
@@ -214,12 +217,15 @@ int check_loss(const cpf_loss_spec* loss) {
 template <typename R>
 int run_unitary(const cpf::Program* prog, int64_t batch, const void* angles, void* u_out, cudaStream_t st) {
   cpf::KParams<R> p;
-  int rc = fill_common(prog, p, batch);
+  // 6-7 qubits: a column per virtual sample on the single-column kernels (engine_impl.cuh: colmode)
+  const bool colmode = prog->n_qubits > 5;
+  int rc = fill_common(prog, p, colmode ? batch << prog->n_qubits : batch, colmode);
   if (rc) return rc;
   p.mode = cpf::M_UNITARY;
+  p.colmode = colmode ? 1 : 0;
   p.angles = (R*)angles; p.u_out = (R*)u_out;
   std::string err;
-  rc = launch_any<R>(p, prog, false, st, err);
+  rc = launch_any<R>(p, prog, colmode, st, err);
   return rc ? fail(rc, err) : CPF_OK;
 }
 

@@ -61,7 +61,9 @@ struct KParams {
   R* aux;           // heis_kernel: [B][n_su2][4] half-angle cos/sin of the 2nd and 3rd fused rotations
   int coef_stride;  // R words per sample in shared memory
   int spb;          // heis_kernel: sample slots used per CTA
+  int colmode;      // engine_kernel<SINGLE>, M_UNITARY: virtual sample b = (sample b / N, column b % N)
   int axp_surface, axp_block;   // heis_kernel: packed rotation axes shared by the surface / block gates
+  int last_slot[8];             // heis_kernel: slot of the last fused gate on each qubit
   PenaltyT<R> pen;
 };
 
@@ -151,6 +153,8 @@ __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, 
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float rsqrt_r(float a) { return rsqrtf(a); }
+__device__ __forceinline__ double rsqrt_r(double a) { return 1.0 / sqrt(a); }
 __device__ __forceinline__ float sqrt_r(float a) { return sqrtf(a); }
 __device__ __forceinline__ double sqrt_r(double a) { return sqrt(a); }
 // 1 - b^t (optax bias correction); float: exp2(t*log2 b), ~1e-7 relative like an f32 pow
@@ -372,6 +376,33 @@ struct Cols {
       const V xr = re[j], xi = im[j];
       re[j] = T::fma(nS, xi, T::mul(C, xr));
       im[j] = T::fma(S, xr, T::mul(C, xi));
+    }
+  }
+  // rows whose bits SET are all set and whose bits CLR are all clear get the phase (c, s)
+  template <int SET, int CLR>
+  static __device__ __forceinline__ void phase_mask(V (&re)[NA], V (&im)[NA], R c, R s) {
+    const V C = T::bc(c), S = T::bc(s), nS = T::bc(-s);
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      if ((j & SET) != SET || (j & CLR) != 0) continue;
+      const V xr = re[j], xi = im[j];
+      re[j] = T::fma(nS, xi, T::mul(C, xr));
+      im[j] = T::fma(S, xr, T::mul(C, xi));
+    }
+  }
+  // real rotation Ry = [[c, -s], [s, c]] on a register bit: 4 FMA per amplitude
+  template <int BP>
+  static __device__ __forceinline__ void ry_reg(V (&re)[NA], V (&im)[NA], R c, R s) {
+    constexpr int M = 1 << BP;
+    const V C = T::bc(c), S = T::bc(s), nS = T::bc(-s);
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      if (j & M) continue;
+      const V xr = re[j], xi = im[j], yr = re[j | M], yi = im[j | M];
+      re[j] = T::fma(nS, yr, T::mul(C, xr));
+      im[j] = T::fma(nS, yi, T::mul(C, xi));
+      re[j | M] = T::fma(C, yr, T::mul(S, xr));
+      im[j | M] = T::fma(C, yi, T::mul(S, xi));
     }
   }
   // ---- CNOT on amplitude-index bit positions (cpos controls, tpos is flipped); `la` is this

@@ -429,13 +429,15 @@ engine_kernel(const KParams<R> p) {
   const long long b = active ? b_raw : p.B - 1;
   const int cg = ls >> LB;                 // column group
   const int la = ls & ((1 << LB) - 1);     // lane part of the amplitude index
-  const int col0 = cg * CPT;
+  // column mode (n >= 6 unitaries): the batch is B * N single-column problems, b = sample * N + column
+  const long long bs = (SINGLE && p.colmode) ? b / N : b;
+  const int col0 = (SINGLE && p.colmode) ? (int)(b % N) : cg * CPT;
   const int P = p.P;
   R* coef = s_coef + (size_t)sl * p.coef_stride;
   R* coef_cp = coef + 8 * p.n_su2;
   const V* tv = reinterpret_cast<const V*>(s_target) + 2 * ((SINGLE ? 0 : cg * (N + 1)) + (la << RB));
 
-  R* ang = p.angles + b * P;   // M_LOSSGRAD/UNITARY/COTANGENT: read-only use
+  R* ang = p.angles + bs * P;   // M_LOSSGRAD/UNITARY/COTANGENT: read-only use
   R* mom = p.m ? p.m + b * P : nullptr;
   R* vel = p.v ? p.v + b * P : nullptr;
   const uint8_t* frz = p.freeze ? p.freeze + b * P : nullptr;
@@ -543,7 +545,7 @@ engine_kernel(const KParams<R> p) {
         for (int r = 0; r < NA; ++r)
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
-            R* dst = p.u_out + ((b * N + ((la << RB) | r)) * N + col0 + k) * 2;
+            R* dst = p.u_out + ((bs * N + ((la << RB) | r)) * N + col0 + k) * 2;
             dst[0] = T::get(pr[r], k); dst[1] = T::get(pi[r], k);
           }
       }

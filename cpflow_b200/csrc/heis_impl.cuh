@@ -77,46 +77,61 @@ struct HeisSweep {
   static __host__ __device__ constexpr int hi_q(int j) { return (int)((HIQ >> (4 * j)) & 15); }
 
   // ------------------------------- forward: row operations on Y -------------------------------
+  // Every fused gate is used in ZYZ form G ~ diag(1, u_out) Ry diag(1, u_in) (global phase dropped: the HS
+  // loss and the Hermitian part that seeds the backward sweep do not see it).  u_in merges with the block's
+  // CP phase and with the u_out still pending on the same qubits into one diagonal (1, B, A, A B e^{ia}),
+  // prepared by the parameter phase: a block costs 3 + 4 + 4 = 11 FMA per amplitude instead of 1 + 8 + 8.
+  // Slot words during the forward sweep: [0,4) alpha, beta; 4 cy; 5 sy; [6,8) u_out; lower-qubit slot
+  // [8,12) A, B; higher-qubit slot [8,10) A B e^{ia}; surface slots [8,10) u_in.
   template <int BP>
-  static __device__ __forceinline__ void su2_fwd(V (&yr)[N], V (&yi)[N], const R* cf) {
-    R c0, c1, c2, c3;
-    Vec4Load<R>::ld(cf, c0, c1, c2, c3);
-    CO::template su2_reg<BP>(yr, yi, c0, c1, c2, c3);
-  }
-  template <int PA, int PB_>
-  static __device__ __forceinline__ void phase_fwd(V (&yr)[N], V (&yi)[N], const R* cf) {
-    CO::template phase<(1 << PA) | (1 << PB_)>(yr, yi, cf[0], cf[1]);
+  static __device__ __forceinline__ void ry_fwd(V (&yr)[N], V (&yi)[N], const R* cf) {
+    CO::template ry_reg<BP>(yr, yi, cf[4], cf[5]);
   }
   template <int Q>
   static __device__ __forceinline__ void surface_fwd(V (&yr)[N], V (&yi)[N], const R* coef) {
     if constexpr (Q < NQ) {
-      su2_fwd<NQ - 1 - Q>(yr, yi, coef + SW * Q);
+      constexpr int BP = NQ - 1 - Q;
+      CO::template phase_mask<(1 << BP), 0>(yr, yi, coef[SW * Q + 8], coef[SW * Q + 9]);
+      ry_fwd<BP>(yr, yi, coef + SW * Q);
       surface_fwd<Q + 1>(yr, yi, coef);
     }
   }
+  template <int Q>
+  static __device__ __forceinline__ void tail_fwd(const KParams<R>& p, V (&yr)[N], V (&yi)[N], const R* coef) {
+    if constexpr (Q < NQ) {
+      const R* cf = coef + SW * p.last_slot[Q];
+      CO::template phase_mask<(1 << (NQ - 1 - Q)), 0>(yr, yi, cf[6], cf[7]);
+      tail_fwd<Q + 1>(p, yr, yi, coef);
+    }
+  }
   template <int J>
-  static __device__ __forceinline__ void blocks_fwd(int k0, int K, const R* cs, const R* cph, V (&yr)[N],
-                                                    V (&yi)[N]) {
+  static __device__ __forceinline__ void blocks_fwd(int k0, int K, const R* cs, V (&yr)[N], V (&yi)[N]) {
     if constexpr (J < NBL) {
       if (k0 + J >= K) return;
       constexpr int PA = NQ - 1 - lo_q(J), PC = NQ - 1 - hi_q(J);
-      phase_fwd<PA, PC>(yr, yi, cph + CW * J);
-      su2_fwd<PA>(yr, yi, cs + 2 * SW * J);
-      su2_fwd<PC>(yr, yi, cs + 2 * SW * J + SW);
-      blocks_fwd<J + 1>(k0, K, cs, cph, yr, yi);
+      const R* cl = cs + 2 * SW * J;
+      const R* ch = cl + SW;
+      R ar, ai, br, bi;
+      Vec4Load<R>::ld(cl + 8, ar, ai, br, bi);
+      CO::template phase_mask<(1 << PA), (1 << PC)>(yr, yi, ar, ai);
+      CO::template phase_mask<(1 << PC), (1 << PA)>(yr, yi, br, bi);
+      CO::template phase_mask<(1 << PA) | (1 << PC), 0>(yr, yi, ch[8], ch[9]);
+      ry_fwd<PA>(yr, yi, cl);
+      ry_fwd<PC>(yr, yi, ch);
+      blocks_fwd<J + 1>(k0, K, cs, yr, yi);
     }
   }
   static __device__ __forceinline__ void forward(const KParams<R>& p, const R* coef, V (&yr)[N], V (&yi)[N]) {
     surface_fwd<0>(yr, yi, coef);
     const int K = p.n_cp;
     const R* cs = coef + SW * NQ;
-    const R* cph = coef + SW * p.n_su2;
 #pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += NBL) {
       __syncthreads();   // keep the warps of the CTA on the same instruction-cache lines
-      blocks_fwd<0>(k0, K, cs, cph, yr, yi);
-      cs += 2 * SW * NBL; cph += CW * NBL;
+      blocks_fwd<0>(k0, K, cs, yr, yi);
+      cs += 2 * SW * NBL;
     }
+    tail_fwd<0>(p, yr, yi, coef);
   }
 
   // ------------------ pivot: gather the x-diagonals, Walsh-Hadamard transform over r ------------------
@@ -476,6 +491,14 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
     su2_lmul_axis(ax2, c2, s2, ar, ai, br, bi);
     cf[0] = ar; cf[1] = ai; cf[2] = br; cf[3] = bi;
     if (u.active) { ax[0] = c1; ax[1] = s1; ax[2] = c2; ax[3] = s2; }
+    // ZYZ form for the forward sweep: alpha = cy p_a, beta = sy p_b, u_out = p_b conj(p_a), u_in = conj(p_a p_b)
+    const R na = ar * ar + ai * ai, nb = br * br + bi * bi;
+    const bool oka = na > R(1e-30), okb = nb > R(1e-30);
+    const R ia = oka ? rsqrt_r(na) : R(0), ib = okb ? rsqrt_r(nb) : R(0);
+    const R par = oka ? ar * ia : R(1), pai = ai * ia, pbr = okb ? br * ib : R(1), pbi = bi * ib;
+    cf[4] = na * ia; cf[5] = nb * ib;
+    cf[6] = pbr * par + pbi * pai; cf[7] = pbi * par - pbr * pai;
+    cf[8] = par * pbr - pai * pbi; cf[9] = -(par * pbi + pai * pbr);
   }
 }
 // packed axes of a gate class: a0 | a1 << 4 | a2 << 8 (15 = unused slot); 0xffff = not uniform
@@ -608,6 +631,23 @@ heis_kernel(const KParams<R> p) {
     }
     __syncwarp();
     if (it == p.nsteps) break;
+    // merged diagonals of the forward sweep: A = pending(lo) u_in(lo), B = pending(hi) u_in(hi), A B e^{ia}
+    for (int k = m; k < p.n_cp; k += TPS) {
+      const CpMeta* md = p.cp + k;
+      R* cl = coef + SW * (NQ + 2 * k);
+      R* ch = cl + SW;
+      const R* pl = coef + SW * md->prev_lo;
+      const R* ph = coef + SW * md->prev_hi;
+      const R* cc = coef_cp + CW * k;
+      const R plr = pl[6], pli = pl[7], phr = ph[6], phi = ph[7];
+      const R ar = plr * cl[8] - pli * cl[9], ai = plr * cl[9] + pli * cl[8];
+      const R br = phr * ch[8] - phi * ch[9], bi = phr * ch[9] + phi * ch[8];
+      const R abr = ar * br - ai * bi, abi = ar * bi + ai * br;
+      const R c = cc[0], s = cc[1];
+      cl[8] = ar; cl[9] = ai; cl[10] = br; cl[11] = bi;
+      ch[8] = abr * c - abi * s; ch[9] = abr * s + abi * c;
+    }
+    __syncwarp();
 
     // ---------------- forward sweep: Y = U V^dag ----------------
     V yr[N], yi[N];

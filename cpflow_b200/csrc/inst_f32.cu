@@ -12,6 +12,8 @@ int launch_engine<float>(const KParams<float>& p, int n, bool single, cudaStream
       case 3: return launch_one<float, 3, 2, 1, true>(p, st, err);
       case 4: return launch_one<float, 4, 2, 1, true>(p, st, err);
       case 5: return launch_one<float, 5, 3, 1, true>(p, st, err);
+      case 6: return launch_one<float, 6, 3, 1, true>(p, st, err);
+      case 7: return launch_one<float, 7, 4, 1, true>(p, st, err);
     }
   } else {
     switch (n) {
@@ -21,14 +23,15 @@ int launch_engine<float>(const KParams<float>& p, int n, bool single, cudaStream
       case 5: return launch_one<float, 5, 4, 2, false>(p, st, err);
     }
   }
-  err = "unsupported number of qubits";
+  err = single ? "unsupported number of qubits"
+               : "full-unitary losses need n <= 5 qubits (6-7 qubits: state preparation and cpf_unitary only)";
   return CPF_ERR_UNSUPPORTED;
 }
 
 template <>
 int engine_rb<float>(int n, bool single) {
   if (single) {
-    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 3; }
+    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 3; case 6: return 3; case 7: return 4; }
   } else {
     switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 4; }
   }

@@ -11,6 +11,8 @@ int launch_engine<double>(const KParams<double>& p, int n, bool single, cudaStre
       case 3: return launch_one<double, 3, 2, 1, true>(p, st, err);
       case 4: return launch_one<double, 4, 2, 1, true>(p, st, err);
       case 5: return launch_one<double, 5, 3, 1, true>(p, st, err);
+      case 6: return launch_one<double, 6, 3, 1, true>(p, st, err);
+      case 7: return launch_one<double, 7, 4, 1, true>(p, st, err);
     }
   } else {
     switch (n) {
@@ -20,14 +22,15 @@ int launch_engine<double>(const KParams<double>& p, int n, bool single, cudaStre
       case 5: return launch_one<double, 5, 5, 1, false>(p, st, err);
     }
   }
-  err = "unsupported number of qubits";
+  err = single ? "unsupported number of qubits"
+               : "full-unitary losses need n <= 5 qubits (6-7 qubits: state preparation and cpf_unitary only)";
   return CPF_ERR_UNSUPPORTED;
 }
 
 template <>
 int engine_rb<double>(int n, bool single) {
   if (single) {
-    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 3; }
+    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 3; case 6: return 3; case 7: return 4; }
   } else {
     switch (n) { case 2: return 2; case 3: return 2; case 4: return 3; case 5: return 5; }
   }

@@ -146,6 +146,14 @@ void detect_layered(Program& p) {
   }
   p.period = period;
   p.layered = true;
+  // pending-phase bookkeeping of the merged-diagonal forward sweep
+  for (int q = 0; q < n; ++q) p.last_slot[q] = q;
+  for (int j = 0; j < K; ++j) {
+    p.cp[j].prev_lo = (int16_t)p.last_slot[lo[j]];
+    p.cp[j].prev_hi = (int16_t)p.last_slot[hi[j]];
+    p.last_slot[lo[j]] = n + 2 * j;
+    p.last_slot[hi[j]] = n + 2 * j + 1;
+  }
 }
 
 DecodedSchedule decode_schedule(const Program& p, int rb) {

@@ -41,6 +41,9 @@ struct CpMeta {
   int32_t pidx;      // -1 = constant angle
   int16_t penalised; // 1 if the default penalty mask covers this parameter
   int16_t is_cz;     // 1: CZ = diag(1,1,1,-1) exactly (no angle)
+  // layered programs: slot of the previous fused gate on the block's lower / higher qubit (its outgoing
+  // Rz phase is still pending when this block starts: heis_impl.cuh, forward with merged diagonals)
+  int16_t prev_lo, prev_hi;
   double cangle;
 };
 
@@ -86,6 +89,7 @@ struct Program {
   bool layered = false;
   int period = 0;
   unsigned long long lo_pack = 0, hi_pack = 0;   // 4 bits per block of the layer
+  int last_slot[16] = {0};                        // slot of the last fused gate on each qubit
   // lazily created per-device copies
   mutable std::mutex mu;
   mutable std::unordered_map<int, DeviceProgram> dev;

@@ -37,7 +37,7 @@ extern "C" {
 #endif
 
 #define CPF_VERSION 100 /* 0.1.0 */
-#define CPF_MAX_QUBITS 5
+#define CPF_MAX_QUBITS 7
 #define CPF_MAX_SEGMENTS 16
 
 typedef enum cpf_status {

@@ -86,3 +86,20 @@ def test_heisenberg_gradient_with_cz_and_constants():
     l, g = H.grad_hs(n, ops, a, tgt)
     l2, g2 = O.hand_adjoint_grad(n, ops, a, "hs", tgt)
     assert abs(l - l2) < 1e-13 and np.abs(g - g2).max() < 1e-13
+
+
+@pytest.mark.parametrize("n,layer,K,rg", [(3, O.chain_layer(3), 5, "xyz"), (4, [[0, 1], [0, 2], [0, 3]], 7, "xz"),
+                                          (4, O.connected_layer(4), 9, "zyx"), (2, [[0, 1]], 3, "xyz")])
+def test_merged_diagonal_forward(n, layer, K, rg):
+    """Forward sweep in ZYZ form with merged diagonals and pending phases (heis_impl.cuh: forward) equals the
+    gate-by-gate forward up to a global phase; the Pauli vector that seeds the backward sweep is identical."""
+    rng = np.random.default_rng(2)
+    anz = O.cp_ansatz(layer, K, rg)
+    ops = O.ansatz_program(anz)
+    tgt = unitary_group.rvs(1 << n, random_state=3)
+    a = rng.uniform(0, 2 * np.pi, anz.num_angles)
+    y, y2 = H.forward(n, ops, a, tgt), H.forward_merged(n, ops, a, tgt)
+    ph = y2.flat[0] / y.flat[0]
+    assert abs(abs(ph) - 1) < 1e-13 and np.abs(y * ph - y2).max() < 1e-13
+    (t1, h1), (t2, h2) = H.to_pauli(y), H.to_pauli(y2)
+    assert abs(abs(t1) - abs(t2)) < 1e-13 and np.abs(h1 - h2).max() < 1e-14

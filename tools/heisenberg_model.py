@@ -184,3 +184,77 @@ def pauli_brute(hm):
                 P = np.kron(P, s)
             out[x, z] = np.real(np.trace(P @ hm))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Forward sweep with merged diagonals (heis_impl.cuh: forward): every fused one-qubit gate is written
+# G ~ diag(1, u_out) Ry diag(1, u_in) (ZYZ form, global phase dropped: the HS loss and its gradient do
+# not see it); u_in merges with the block's CP phase and with the pending u_out of the previous gate on
+# the same qubit into one two-qubit diagonal (1, B, A, A B e^{ia}); u_out stays pending.
+# ---------------------------------------------------------------------------------------------
+def zyz(g):
+    al, be = g[0, 0], g[1, 0]
+    cy, sy = abs(al), abs(be)
+    pa = al / cy if cy > 1e-150 else 1.0
+    pb = be / sy if sy > 1e-150 else 1.0
+    return cy, sy, np.conj(pa * pb), pb * np.conj(pa)      # cy, sy, u_in, u_out
+
+
+def layered_structure(n, ops, angles):
+    """Fused gates of a layered template: surface[q] = 2x2, blocks = [(lo, hi, cp_phase, g_lo, g_hi)]."""
+    def fuse(seq):
+        g = np.eye(2, dtype=complex)
+        for kind, a in seq:
+            g = rot_mat(kind, a) @ g
+        return g
+    pend = {q: [] for q in range(n)}
+    surface, blocks = {}, []
+    cur = None
+    for kind, q0, q1, pi, const in ops:
+        a = angles[pi] if pi >= 0 else const
+        if kind in (RX, RY, RZ):
+            pend[q0].append((kind, a))
+        else:
+            if cur is None:
+                surface = {q: fuse(pend[q]) for q in range(n)}
+            else:
+                blocks.append((cur[0], cur[1], cur[2], fuse(pend[cur[0]]), fuse(pend[cur[1]])))
+            for q in (q0, q1) if cur is None else cur[:2]:
+                pend[q] = []
+            if cur is None:
+                pend = {q: [] for q in range(n)}
+            lo, hi = min(q0, q1), max(q0, q1)
+            cur = (lo, hi, np.exp(1j * a) if kind == CP else -1.0)
+    if cur is None:
+        surface = {q: fuse(pend[q]) for q in range(n)}
+    else:
+        blocks.append((cur[0], cur[1], cur[2], fuse(pend[cur[0]]), fuse(pend[cur[1]])))
+    return surface, blocks
+
+
+def forward_merged(n, ops, angles, target):
+    """Y' = e^{i gamma} U V^dag through Ry rotations and merged diagonals only."""
+    N = 1 << n
+    y = np.conj(np.asarray(target, dtype=complex)).T.copy()
+    idx = np.arange(N)
+    bit = lambda q: (idx >> (n - 1 - q)) & 1
+    surface, blocks = layered_structure(n, ops, angles)
+    pending = {}
+    for q in range(n):
+        cy, sy, u_in, u_out = zyz(surface[q])
+        y[bit(q) == 1] *= u_in
+        apply_row(y, np.array([[cy, -sy], [sy, cy]]), n - 1 - q)
+        pending[q] = u_out
+    for lo, hi, cp, g_lo, g_hi in blocks:
+        cl, sl, uil, uol = zyz(g_lo)
+        ch, sh, uih, uoh = zyz(g_hi)
+        A, Bv = pending[lo] * uil, pending[hi] * uih
+        y[(bit(lo) == 1) & (bit(hi) == 0)] *= A
+        y[(bit(lo) == 0) & (bit(hi) == 1)] *= Bv
+        y[(bit(lo) == 1) & (bit(hi) == 1)] *= A * Bv * cp
+        apply_row(y, np.array([[cl, -sl], [sl, cl]]), n - 1 - lo)
+        apply_row(y, np.array([[ch, -sh], [sh, ch]]), n - 1 - hi)
+        pending[lo], pending[hi] = uol, uoh
+    for q in range(n):
+        y[bit(q) == 1] *= pending[q]
+    return y
