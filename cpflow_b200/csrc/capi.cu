@@ -184,7 +184,11 @@ int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams
   int rc = cpf::launch_pack_target_heis<R>((const R*)loss->target, *packed, prog->n_qubits, cpt, st);
   if (rc) return fail(rc, "pack_target_heis launch failed");
   const size_t aux_bytes = (size_t)p.B * (prog->su2.empty() ? 1 : prog->su2.size()) * 4 * sizeof(R);
-  CPF_CUDA(cudaMallocAsync((void**)aux, aux_bytes, st));
+  // one allocation: per-gate scratch, then the packed optimiser state (32-byte aligned)
+  const size_t aux_pad = (aux_bytes + 31) & ~(size_t)31;
+  const size_t pk_bytes = (size_t)p.B * (prog->n_params > 0 ? prog->n_params : 1) * 4 * sizeof(R);
+  CPF_CUDA(cudaMallocAsync((void**)aux, aux_pad + pk_bytes, st));
+  p.pk = reinterpret_cast<char*>(*aux) + aux_pad;
   p.target_packed = *packed;
   p.target_bytes = (int)bytes;
   p.loss_kind = loss->kind;

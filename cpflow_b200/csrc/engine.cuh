@@ -58,6 +58,7 @@ struct KParams {
   R* hist_params; R* hist_regloss; long long hist_len;
   R* loss_out; R* reg_out; R* grad_out;
   R* u_out; const R* cot;
+  void* pk;         // heis_kernel: [B][P] packed optimiser state {theta, m, v, best} (heis_impl.cuh: Pk4)
   R* aux;           // heis_kernel: [B][n_su2][4] half-angle cos/sin of the 2nd and 3rd fused rotations
   int coef_stride;  // R words per sample in shared memory
   int spb;          // heis_kernel: sample slots used per CTA

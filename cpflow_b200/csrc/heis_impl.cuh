@@ -342,12 +342,31 @@ struct UpdCtx {
   bool active;          // this thread's sample exists
   bool store_best;      // the step being finished improved on the best regloss: keep its parameters
   bool skip_coef;       // last pass: no new coefficients
-  bool first;           // step 0: the Adam moments start from zero (not read)
   bool hist;            // parameter history is recorded for this step
   unsigned off;         // b * P
   size_t hist_off;      // (b * hist_len + gu + 1) * P
   R bc1, bc2, ibc1, ibc2;
 };
+
+// Optimiser state of one parameter, packed so that the update phase moves it with one 16-byte (float) or two
+// 16-byte (double) accesses: theta, Adam moments, best-regloss parameter.  The kernel packs the caller's
+// separate arrays (include/cpflow_b200.h: cpf_adam_buffers) into this scratch at launch and unpacks at the end.
+template <typename R> struct __align__(4 * sizeof(R) > 16 ? 16 : 4 * sizeof(R)) Pk4 { R th, mu, nu, best; };
+__device__ __forceinline__ Pk4<float> pk_load(const Pk4<float>* q) {
+  const float4 t = *reinterpret_cast<const float4*>(q);
+  return {t.x, t.y, t.z, t.w};
+}
+__device__ __forceinline__ void pk_store(Pk4<float>* q, const Pk4<float>& v) {
+  *reinterpret_cast<float4*>(q) = make_float4(v.th, v.mu, v.nu, v.best);
+}
+__device__ __forceinline__ Pk4<double> pk_load(const Pk4<double>* q) {
+  const double2 a = reinterpret_cast<const double2*>(q)[0], b = reinterpret_cast<const double2*>(q)[1];
+  return {a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void pk_store(Pk4<double>* q, const Pk4<double>& v) {
+  reinterpret_cast<double2*>(q)[0] = make_double2(v.th, v.mu);
+  reinterpret_cast<double2*>(q)[1] = make_double2(v.nu, v.best);
+}
 
 static __device__ __noinline__ SinCos<float> sincos_slow_v(float x) { float s, c; sincosf(x, &s, &c); return {s, c}; }
 // sin/cos for the parameter phase, inlined so the three evaluations of a fused gate interleave
@@ -392,21 +411,19 @@ __device__ __forceinline__ void adam_inl(const KParams<float>& p, const UpdCtx<f
   th = add_rn(th, mul_rn(-p.lr, __fdividef(mu_hat, add_rn(rt, p.eps))));
 }
 
-// one parameter: gradient sink (loss_grad mode) or best-parameter bookkeeping + Adam step
+// one parameter: gradient sink (loss_grad mode) or best-parameter bookkeeping + Adam step on the packed state
 template <typename R>
-__device__ __forceinline__ void heis_apply(const KParams<R>& p, const UpdCtx<R>& u, int pi, R g, R& th, R mu, R nu) {
-  const unsigned idx = u.off + (unsigned)pi;
+__device__ __forceinline__ void heis_apply(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int pi, R g, Pk4<R>& v) {
   if (u.phase == PH_GRAD) {
-    if (u.active) p.grad_out[idx] = g;
+    if (u.active) p.grad_out[u.off + (unsigned)pi] = g;
     return;
   }
-  // th is still the pre-update parameter of the step being finished (optimization.py:70-73)
-  if (u.store_best && u.active) p.best_params[idx] = th;
-  if (p.freeze && p.freeze[idx]) return;
-  adam_inl(p, u, g, th, mu, nu);
+  // v.th is still the pre-update parameter of the step being finished (optimization.py:70-73)
+  if (u.store_best) v.best = v.th;
+  if (!(p.freeze && p.freeze[u.off + (unsigned)pi])) adam_inl(p, u, g, v.th, v.mu, v.nu);
   if (u.active) {
-    p.m[idx] = mu; p.v[idx] = nu; p.angles[idx] = th;
-    if (u.hist) p.hist_params[u.hist_off + pi] = th;
+    pk_store(pk + pi, v);
+    if (u.hist) p.hist_params[u.hist_off + pi] = v.th;
   }
 }
 
@@ -431,26 +448,22 @@ __device__ __forceinline__ void su2_lmul_axis(int a, R c, R s, R& ar, R& ai, R& 
 template <typename R>
 struct GateIn {
   int pi0, pi1, pi2;
-  R th0, th1, th2, mu0, nu0, mu1, nu1, mu2, nu2, sx, sy, sz, c2, s2, c3, s3;
+  Pk4<R> v0, v1, v2;
+  R sx, sy, sz, c2, s2, c3, s3;
 };
 template <typename R>
-__device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const UpdCtx<R>& u, bool valid,
+__device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const UpdCtx<R>& u, const Pk4<R>* pk, bool valid,
                                                     const Su2Meta* md, const R* cf, const R* ax) {
   GateIn<R> in;
   in.pi0 = in.pi1 = in.pi2 = -1;
-  in.th0 = in.th1 = in.th2 = in.mu0 = in.nu0 = in.mu1 = in.nu1 = in.mu2 = in.nu2 = R(0);
+  in.v0 = in.v1 = in.v2 = Pk4<R>{R(0), R(0), R(0), R(0)};
   in.sx = in.sy = in.sz = in.c2 = in.s2 = in.c3 = in.s3 = R(0);
   if (!valid) return in;
   in.pi0 = md->pidx[0]; in.pi1 = md->pidx[1]; in.pi2 = md->pidx[2];
-  if (in.pi0 >= 0) in.th0 = p.angles[u.off + (unsigned)in.pi0]; else in.th0 = R(md->cangle[0]);
-  if (in.pi1 >= 0) in.th1 = p.angles[u.off + (unsigned)in.pi1]; else in.th1 = R(md->cangle[1]);
-  if (in.pi2 >= 0) in.th2 = p.angles[u.off + (unsigned)in.pi2]; else in.th2 = R(md->cangle[2]);
+  if (in.pi0 >= 0) in.v0 = pk_load(pk + in.pi0); else in.v0.th = R(md->cangle[0]);
+  if (in.pi1 >= 0) in.v1 = pk_load(pk + in.pi1); else in.v1.th = R(md->cangle[1]);
+  if (in.pi2 >= 0) in.v2 = pk_load(pk + in.pi2); else in.v2.th = R(md->cangle[2]);
   if (u.phase != PH_COEF) {
-    if (u.phase == PH_ADAM && !u.first) {
-      if (in.pi0 >= 0) { in.mu0 = p.m[u.off + (unsigned)in.pi0]; in.nu0 = p.v[u.off + (unsigned)in.pi0]; }
-      if (in.pi1 >= 0) { in.mu1 = p.m[u.off + (unsigned)in.pi1]; in.nu1 = p.v[u.off + (unsigned)in.pi1]; }
-      if (in.pi2 >= 0) { in.mu2 = p.m[u.off + (unsigned)in.pi2]; in.nu2 = p.v[u.off + (unsigned)in.pi2]; }
-    }
     in.sx = cf[3]; in.sy = cf[7]; in.sz = cf[11];
     Vec4Load<R>::ld(ax, in.c2, in.s2, in.c3, in.s3);
   }
@@ -460,7 +473,7 @@ __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const U
 // Fused one-qubit gate: finish the step (chain rule through the fusion, Adam), then the new (alpha, beta).
 // AX* >= 0: compile-time rotation axes (the selects fold away); AX0 == -2: axes from the gate metadata.
 template <typename R, int AX0, int AX1, int AX2>
-__device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, const Su2Meta* md,
+__device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, const Su2Meta* md,
                                                 GateIn<R> in, R* cf, R* ax) {
   const int ax0 = AX0 == -2 ? md->axis[0] : AX0;
   const int ax1 = AX0 == -2 ? md->axis[1] : AX1;
@@ -476,15 +489,15 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
     const R g2 = sel3(ax2, in.sx, in.sy, in.sz);
     const R g1 = x1 * in.sx + y1 * in.sy + z1 * in.sz;
     const R g0 = x0 * in.sx + y0 * in.sy + z0 * in.sz;
-    if (in.pi2 >= 0) heis_apply(p, u, in.pi2, g2, in.th2, in.mu2, in.nu2);
-    if (in.pi1 >= 0) heis_apply(p, u, in.pi1, g1, in.th1, in.mu1, in.nu1);
-    if (in.pi0 >= 0) heis_apply(p, u, in.pi0, g0, in.th0, in.mu0, in.nu0);
+    if (in.pi2 >= 0) heis_apply(p, u, pk, in.pi2, g2, in.v2);
+    if (in.pi1 >= 0) heis_apply(p, u, pk, in.pi1, g1, in.v1);
+    if (in.pi0 >= 0) heis_apply(p, u, pk, in.pi0, g0, in.v0);
   }
   if (!u.skip_coef) {
     R c0 = R(1), s0 = R(0), c1 = R(1), s1 = R(0), c2 = R(1), s2 = R(0);
-    if (ax0 >= 0) sincos_inl(in.th0 * R(0.5), s0, c0);
-    if (ax1 >= 0) sincos_inl(in.th1 * R(0.5), s1, c1);
-    if (ax2 >= 0) sincos_inl(in.th2 * R(0.5), s2, c2);
+    if (ax0 >= 0) sincos_inl(in.v0.th * R(0.5), s0, c0);
+    if (ax1 >= 0) sincos_inl(in.v1.th * R(0.5), s1, c1);
+    if (ax2 >= 0) sincos_inl(in.v2.th * R(0.5), s2, c2);
     R ar, ai, br, bi;
     su2_of(ax0, c0, s0, ar, ai, br, bi);
     su2_lmul_axis(ax1, c1, s1, ar, ai, br, bi);
@@ -508,25 +521,25 @@ constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
 
 // gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined
 template <typename R, int AX0, int AX1, int AX2>
-__device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const UpdCtx<R>& u, int g0, int g_end, int stride,
-                                              R* coef, R* aux) {
+__device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end,
+                                              int stride, R* coef, R* aux) {
   constexpr int SW = HEIS_SU2_WORDS;
-  GateIn<R> cur = heis_gate_load(p, u, g0 < g_end, p.su2 + g0, coef + SW * g0, aux + 4 * g0);
+  GateIn<R> cur = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, coef + SW * g0, aux + 4 * g0);
 #pragma unroll 1
   for (int g = g0; g < g_end; g += stride) {
     const int gn = g + stride;
-    const GateIn<R> nxt = heis_gate_load(p, u, gn < g_end, p.su2 + gn, coef + SW * gn, aux + 4 * gn);
-    heis_su2_update<R, AX0, AX1, AX2>(p, u, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
+    const GateIn<R> nxt = heis_gate_load(p, u, pk, gn < g_end, p.su2 + gn, coef + SW * gn, aux + 4 * gn);
+    heis_su2_update<R, AX0, AX1, AX2>(p, u, pk, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
     cur = nxt;
   }
 }
 template <typename R>
-__device__ __forceinline__ void heis_su2_loop_any(int axp, const KParams<R>& p, const UpdCtx<R>& u, int g0, int g_end,
-                                                  int stride, R* coef, R* aux) {
-  if (axp == AXP_XYZ) heis_su2_loop<R, 0, 1, 2>(p, u, g0, g_end, stride, coef, aux);
-  else if (axp == AXP_ZXZ) heis_su2_loop<R, 2, 0, 2>(p, u, g0, g_end, stride, coef, aux);
-  else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1>(p, u, g0, g_end, stride, coef, aux);
-  else heis_su2_loop<R, -2, -2, -2>(p, u, g0, g_end, stride, coef, aux);
+__device__ __forceinline__ void heis_su2_loop_any(int axp, const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int g0,
+                                                  int g_end, int stride, R* coef, R* aux) {
+  if (axp == AXP_XYZ) heis_su2_loop<R, 0, 1, 2>(p, u, pk, g0, g_end, stride, coef, aux);
+  else if (axp == AXP_ZXZ) heis_su2_loop<R, 2, 0, 2>(p, u, pk, g0, g_end, stride, coef, aux);
+  else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1>(p, u, pk, g0, g_end, stride, coef, aux);
+  else heis_su2_loop<R, -2, -2, -2>(p, u, pk, g0, g_end, stride, coef, aux);
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -572,6 +585,20 @@ heis_kernel(const KParams<R> p) {
 
   const unsigned off = (unsigned)(b * P);   // host: B * P < 2^32
   R* aux = p.aux + (size_t)b * p.n_su2 * 4;
+  Pk4<R>* pk = reinterpret_cast<Pk4<R>*>(p.pk) + off;
+  {
+    // pack this sample's optimiser state (a resumed run, step0 > 0, carries its moments and best parameters)
+    const bool resume = p.mode == M_ADAM && p.step0 > 0;
+    for (int i = m; i < P; i += TPS) {
+      Pk4<R> v;
+      v.th = p.angles[off + i];
+      v.mu = resume ? p.m[off + i] : R(0);
+      v.nu = resume ? p.v[off + i] : R(0);
+      v.best = resume ? p.best_params[off + i] : v.th;
+      if (active) pk_store(pk + i, v);
+    }
+    __syncwarp();
+  }
   const R NN = R(N) * R(N);
 
   R best = R(0), best_reg_v = R(0);
@@ -587,7 +614,6 @@ heis_kernel(const KParams<R> p) {
       UpdCtx<R> u;
       u.phase = phase; u.active = active; u.off = off;
       const long long gu = gi - 1;
-      u.first = gu == 0;
       u.store_best = improved_prev && p.mode == M_ADAM && phase == PH_ADAM;
       u.skip_coef = it == p.nsteps;
       u.hist = p.hist_params != nullptr && gu + 1 < p.hist_len;
@@ -599,22 +625,19 @@ heis_kernel(const KParams<R> p) {
         u.ibc1 = R(1) / u.bc1; u.ibc2 = R(1) / u.bc2;
       }
       // surface gates (slots < NQ) and block gates (the rest) each share one axis pattern in the templates
-      heis_su2_loop_any(p.axp_surface, p, u, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
-      heis_su2_loop_any(p.axp_block, p, u, NQ + m, p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any(p.axp_surface, p, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any(p.axp_block, p, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
       for (int k = m; k < p.n_cp; k += TPS) {
         const CpMeta* md = p.cp + k;
         R* cf = coef_cp + CW * k;
         const int pi = md->pidx;
         const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
                             (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
-        R th;
-        if (pi >= 0) th = p.angles[off + (unsigned)pi]; else th = R(md->cangle);
-        if (phase != PH_COEF && pi >= 0) {
-          R mu = R(0), nu = R(0);
-          if (phase == PH_ADAM && !u.first) { mu = p.m[off + (unsigned)pi]; nu = p.v[off + (unsigned)pi]; }
-          // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
-          heis_apply(p, u, pi, add_rn(cf[0], cf[2]), th, mu, nu);
-        }
+        Pk4<R> v;
+        if (pi >= 0) v = pk_load(pk + pi); else v.th = R(md->cangle);
+        // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
+        if (phase != PH_COEF && pi >= 0) heis_apply(p, u, pk, pi, add_rn(cf[0], cf[2]), v);
+        const R th = v.th;
         if (!u.skip_coef) {
           R s = R(0), c = R(-1);                 // CZ = diag(1,1,1,-1) exactly
           if (!md->is_cz) sincos_inl(th, s, c);
@@ -716,9 +739,13 @@ heis_kernel(const KParams<R> p) {
     __syncwarp();
   }
 
-  if (p.mode == M_ADAM && active && m == 0) {
-    p.best_regloss[b] = best;
-    p.best_reg[b] = best_reg_v;
+  if (p.mode == M_ADAM && active) {
+    // unpack the optimiser state into the caller's arrays
+    for (int i = m; i < P; i += TPS) {
+      const Pk4<R> v = pk_load(pk + i);
+      p.angles[off + i] = v.th; p.m[off + i] = v.mu; p.v[off + i] = v.nu; p.best_params[off + i] = v.best;
+    }
+    if (m == 0) { p.best_regloss[b] = best; p.best_reg[b] = best_reg_v; }
   }
 }
 
