@@ -29,7 +29,7 @@
 namespace cpf {
 
 constexpr int HEIS_SU2_WORDS = 12;   // alpha,beta (fwd) -> M rows padded to float4 (bwd); pads 3,7,11 = S
-constexpr int HEIS_CP_WORDS = 4;     // cos, sin, r * penalty slope, - ; word 0 <- dL/da after the backward sweep
+constexpr int HEIS_CP_WORDS = 4;     // cos(a/2), sin(a/2), r * penalty slope, - ; word 0 <- dL/da after the backward sweep
 
 inline int heis_coef_stride(int n_su2, int n_cp) {
   int w = (HEIS_SU2_WORDS * n_su2 + HEIS_CP_WORDS * n_cp + 3) & ~3;
@@ -223,28 +223,19 @@ struct HeisSweep {
   template <int B>
   static __device__ __forceinline__ bool xlane(int m) { return ((m >> (B - PB)) & 1) != 0; }
 
-  // CP / CZ gate on amplitude bits (B1, B2).  Quad e[z1][z2] at fixed x and other z bits; by the x bits of
-  // the two qubits: (1,0) pairs (e00,e01),(e10,e11); (0,1) pairs (e00,e10),(e01,e11); (1,1) pairs
-  // (e00,e11) and the SUM pair (e01,e10); (0,0) untouched.  The pair differences rotate by the CP angle.
+  // Entangler of a block on amplitude bits (B1, B2).  CP(a) ~ Rz_1(a/2) Rz_2(a/2) exp(i (a/4) Z1 Z2): the two Rz
+  // are folded into the SO(3) matrices of the block's fused gates (heis_su2_to_so3), what remains rotates,
+  // for coefficients whose x bits on the two qubits differ, the pairs (e00, e11) and (e01, e10) of every
+  // (z1, z2) quad by a/2.  cf: cos(a/2), sin(a/2); word 0 receives dL/da = -(h_II - h_ZI - h_IZ + h_ZZ)/2
+  // (Z-type coefficients: they do not see the Rz shuffle).
   template <typename E>
-  static __device__ __forceinline__ void cp_quad(E& e00, E& e01, E& e10, E& e11, bool isB, bool isC, E kcl, E ksl,
-                                                 E nsg) {
+  static __device__ __forceinline__ void zz_quad(E& e00, E& e01, E& e10, E& e11, E cl, E sl, E s2) {
     using O = VT<R, sizeof(E) == sizeof(R) ? 1 : 2>;
-    auto sel = [](bool pr, E a, E b) {
-      if constexpr (sizeof(E) == sizeof(R)) return pr ? a : b;
-      else return O::make(pr ? a.x : b.x, pr ? a.y : b.y);
-    };
-    E f01 = sel(isB, e10, sel(isC, e11, e01));
-    E f10 = sel(isB, e01, e10);
-    E f11 = sel(isC, e01, e11);
-    const E v1 = O::sub(e00, f01), v2 = O::fma(nsg, f11, f10);          // f10 - sg * f11
-    const E d1 = O::fma(ksl, v2, O::mul(kcl, v1));                      // kc v1 + ks v2
-    const E d2 = O::sub(O::mul(kcl, v2), O::mul(ksl, v1));              // kc v2 - ks v1
-    e00 = AddV<E>::add(e00, d1); f01 = O::sub(f01, d1);
-    f10 = AddV<E>::add(f10, d2); f11 = O::fma(nsg, d2, f11);            // f11 - sg * d2
-    e01 = sel(isB, f10, sel(isC, f11, f01));
-    e10 = sel(isB, f01, f10);
-    e11 = sel(isC, f01, f11);
+    const E a = e00, b = e01, c = e10, d = e11;
+    e00 = O::sub(O::mul(cl, a), O::mul(sl, d));
+    e11 = O::fma(sl, a, O::mul(cl, d));
+    e01 = O::sub(O::mul(cl, b), O::mul(s2, c));
+    e10 = O::fma(s2, b, O::mul(cl, c));
   }
   template <int B1, int B2>
   static __device__ __forceinline__ void phase_bwd(V (&hv)[N], R* cf, int m) {
@@ -253,16 +244,14 @@ struct HeisSweep {
     const R g11 = R(-0.5) * ((T::get(hv[0], 0) - T::get(hv[M1], 0)) - (T::get(hv[M2], 0) - T::get(hv[M1 | M2], 0)));
     __syncwarp();
     if (m == 0) cf[0] = g11;
-    const R kc = R(0.5) * (c - R(1)), ks = R(0.5) * s;
     if constexpr (B1 >= PB && B2 >= PB) {
-      // both x bits are lane bits: one group per lane, packed arithmetic over xr
-      const bool x1 = xlane<B1>(m), x2 = xlane<B2>(m);
-      const bool isB = !x1 && x2, isC = x1 && x2, on = x1 || x2;
-      const V kcl = T::bc(on ? kc : R(0)), ksl = T::bc(on ? ks : R(0)), nsg = T::bc(isC ? R(1) : R(-1));
+      // both x bits are lane bits: one case per lane, packed arithmetic over xr
+      const bool x1 = xlane<B1>(m), x2 = xlane<B2>(m), on = x1 != x2;
+      const V cl = T::bc(on ? c : R(1)), sl = T::bc(on ? s : R(0)), s2 = T::bc(on ? (x1 ? s : -s) : R(0));
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & (M1 | M2)) continue;
-        cp_quad<V>(hv[z], hv[z | M2], hv[z | M1], hv[z | M1 | M2], isB, isC, kcl, ksl, nsg);
+        zz_quad<V>(hv[z], hv[z | M2], hv[z | M1], hv[z | M1 | M2], cl, sl, s2);
       }
     } else {
       // one of the bits is amplitude bit 0, whose x bit is the packed component xr: scalar per component
@@ -270,15 +259,14 @@ struct HeisSweep {
       const bool xl = xlane<BL>(m);
 #pragma unroll
       for (int xr = 0; xr < XR; ++xr) {
-        const bool x1 = B1 >= PB ? xl : xr != 0, x2 = B2 >= PB ? xl : xr != 0;
-        const bool isB = !x1 && x2, isC = x1 && x2, on = x1 || x2;
-        const R kcl = on ? kc : R(0), ksl = on ? ks : R(0), nsg = isC ? R(1) : R(-1);
+        const bool x1 = B1 >= PB ? xl : xr != 0, x2 = B2 >= PB ? xl : xr != 0, on = x1 != x2;
+        const R cl = on ? c : R(1), sl = on ? s : R(0), s2 = on ? (x1 ? s : -s) : R(0);
 #pragma unroll
         for (int z = 0; z < N; ++z) {
           if (z & (M1 | M2)) continue;
           R e00 = T::get(hv[z], xr), e01 = T::get(hv[z | M2], xr), e10 = T::get(hv[z | M1], xr),
             e11 = T::get(hv[z | M1 | M2], xr);
-          cp_quad<R>(e00, e01, e10, e11, isB, isC, kcl, ksl, nsg);
+          zz_quad<R>(e00, e01, e10, e11, cl, sl, s2);
           setc(hv[z], xr, e00); setc(hv[z | M2], xr, e01); setc(hv[z | M1], xr, e10); setc(hv[z | M1 | M2], xr, e11);
         }
       }
@@ -323,11 +311,15 @@ struct HeisSweep {
 // SO(3) matrix of G = [[alpha, -conj(beta)], [beta, conj(alpha)]] = w - i (x sx + y sy + z sz), stored
 // transposed (M = R^T) in rows of 4 words; the pad words are left alone (they carry the gradient sums).
 template <typename R>
-__device__ __forceinline__ void heis_su2_to_so3(R* cf) {
+__device__ __forceinline__ void heis_su2_to_so3(R* cf, R ch, R sh) {
   const R w = cf[0], z = -cf[1], y = cf[2], x = -cf[3];
   const R xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
-  cf[0] = R(1) - R(2) * (yy + zz); cf[1] = R(2) * (xy + wz); cf[2] = R(2) * (xz - wy);
-  cf[4] = R(2) * (xy - wz); cf[5] = R(1) - R(2) * (xx + zz); cf[6] = R(2) * (yz + wx);
+  // rows of M = R(G)^T
+  const R x0 = R(1) - R(2) * (yy + zz), x1 = R(2) * (xy + wz), x2 = R(2) * (xz - wy);
+  const R y0 = R(2) * (xy - wz), y1 = R(1) - R(2) * (xx + zz), y2 = R(2) * (yz + wx);
+  // G' = G Rz(a/2) (the block's share of its CP gate, applied before G): M' = Rz3(-a/2) M mixes rows X and Y
+  cf[0] = ch * x0 + sh * y0; cf[1] = ch * x1 + sh * y1; cf[2] = ch * x2 + sh * y2;
+  cf[4] = ch * y0 - sh * x0; cf[5] = ch * y1 - sh * x1; cf[6] = ch * y2 - sh * x2;
   cf[8] = R(2) * (xz + wy); cf[9] = R(2) * (yz - wx); cf[10] = R(1) - R(2) * (xx + yy);
 }
 
@@ -639,8 +631,8 @@ heis_kernel(const KParams<R> p) {
         if (phase != PH_COEF && pi >= 0) heis_apply(p, u, pk, pi, add_rn(cf[0], cf[2]), v);
         const R th = v.th;
         if (!u.skip_coef) {
-          R s = R(0), c = R(-1);                 // CZ = diag(1,1,1,-1) exactly
-          if (!md->is_cz) sincos_inl(th, s, c);
+          R s = R(1), c = R(0);                  // half angle; CZ = CP(pi): cos(pi/2) = 0 exactly
+          if (!md->is_cz) sincos_inl(th * R(0.5), s, c);
           R rs = R(0);
           if (pen_on) {
             R val, slope;
@@ -666,7 +658,7 @@ heis_kernel(const KParams<R> p) {
       const R ar = plr * cl[8] - pli * cl[9], ai = plr * cl[9] + pli * cl[8];
       const R br = phr * ch[8] - phi * ch[9], bi = phr * ch[9] + phi * ch[8];
       const R abr = ar * br - ai * bi, abi = ar * bi + ai * br;
-      const R c = cc[0], s = cc[1];
+      const R c = cc[0] * cc[0] - cc[1] * cc[1], s = R(2) * cc[0] * cc[1];   // e^{ia} from the half angle
       cl[8] = ar; cl[9] = ai; cl[10] = br; cl[11] = bi;
       ch[8] = abr * c - abi * s; ch[9] = abr * s + abi * c;
     }
@@ -731,7 +723,10 @@ heis_kernel(const KParams<R> p) {
     }
     // fused-gate coefficients (alpha, beta) -> SO(3) rows, in place (the forward sweep is done with them)
     __syncwarp();
-    for (int g = m; g < p.n_su2; g += TPS) heis_su2_to_so3(coef + SW * g);
+    for (int g = m; g < p.n_su2; g += TPS) {
+      const R* cc = coef_cp + CW * ((g - NQ) >> 1);      // block gates carry half of their CP gate's Rz
+      heis_su2_to_so3(coef + SW * g, g >= NQ ? cc[0] : R(1), g >= NQ ? cc[1] : R(0));
+    }
     __syncwarp();
 
     // ---------------- Heisenberg sweep ----------------

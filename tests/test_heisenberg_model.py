@@ -103,3 +103,27 @@ def test_merged_diagonal_forward(n, layer, K, rg):
     assert abs(abs(ph) - 1) < 1e-13 and np.abs(y * ph - y2).max() < 1e-13
     (t1, h1), (t2, h2) = H.to_pauli(y), H.to_pauli(y2)
     assert abs(abs(t1) - abs(t2)) < 1e-13 and np.abs(h1 - h2).max() < 1e-14
+
+
+def test_zz_split_of_the_cp_gate():
+    """CP(a) ~ Rz Rz exp(i a/4 ZZ): the pair rotation of the ZZ part against brute force, and the full gradient
+    with the Rz halves folded into the block's fused gates (the kernel's backward sweep) against the oracle."""
+    rng = np.random.default_rng(2)
+    N = 8
+    y = rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))
+    Hm = (y + y.conj().T) / 2
+    hb = H.pauli_brute(Hm)
+    idx = np.arange(N)
+    for b1, b2 in [(0, 1), (1, 0), (2, 0), (1, 2)]:
+        zz = np.array([(1 - 2 * ((i >> b1) & 1)) * (1 - 2 * ((i >> b2) & 1)) for i in idx])
+        U = np.diag(np.exp(1j * (0.77 / 4) * zz))
+        assert np.abs(H.conj_zz(hb, 0.77, b1, b2) - H.pauli_brute(U.conj().T @ Hm @ U)).max() < 1e-14
+    for n, layer, K, rg in [(3, O.chain_layer(3), 5, "xyz"), (4, [[0, 1], [0, 2], [0, 3]], 7, "xz"),
+                            (4, O.connected_layer(4), 9, "zyx")]:
+        anz = O.cp_ansatz(layer, K, rg)
+        ops = O.ansatz_program(anz)
+        tgt = unitary_group.rvs(1 << n, random_state=3)
+        a = rng.uniform(0, 2 * np.pi, anz.num_angles)
+        l, g = H.grad_hs_zz(n, ops, a, tgt)
+        l2, g2 = O.hand_adjoint_grad(n, ops, a, "hs", tgt)
+        assert abs(l - l2) < 1e-13 and np.abs(g - g2).max() < 1e-13

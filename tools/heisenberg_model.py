@@ -258,3 +258,67 @@ def forward_merged(n, ops, angles, target):
     for q in range(n):
         y[bit(q) == 1] *= pending[q]
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# Backward sweep with the CP gate split as CP(a) ~ Rz_lo(a/2) Rz_hi(a/2) exp(i (a/4) Z Z): the two Rz are
+# absorbed into the SO(3) matrices of the block's fused gates (M' = Rz3(-a/2) M), what is left of the CP gate
+# is a plain pair rotation by a/2 (no group-dependent pairing): heis_impl.cuh, zz_bwd.
+# ---------------------------------------------------------------------------------------------
+def conj_zz(h, a, bit1, bit2):
+    """h <- coefficients of ZZ'^dag H ZZ', ZZ' = exp(i (a/4) Z1 Z2)."""
+    N = h.shape[0]
+    b1, b2 = 1 << bit1, 1 << bit2
+    c, s = math.cos(a / 2), math.sin(a / 2)
+    out = h.copy()
+    for x in range(N):
+        x1, x2 = (x & b1) != 0, (x & b2) != 0
+        if x1 == x2:
+            continue
+        sg = 1.0 if x1 else -1.0
+        for z in range(N):
+            if z & (b1 | b2):
+                continue
+            e00, e01, e10, e11 = h[x, z], h[x, z | b2], h[x, z | b1], h[x, z | b1 | b2]
+            out[x, z] = c * e00 - s * e11
+            out[x, z | b1 | b2] = c * e11 + s * e00
+            out[x, z | b2] = c * e01 - sg * s * e10
+            out[x, z | b1] = c * e10 + sg * s * e01
+    return out
+
+
+def grad_hs_zz(n, ops, angles, target):
+    """Same gradient as grad_hs for a layered template, with the Rz halves of every CP gate fused into the
+    block's one-qubit gates (checks the bookkeeping of the kernel's backward sweep)."""
+    N = 1 << n
+    y = forward_merged(n, ops, angles, target)
+    t, h = to_pauli(y)
+    loss = 1 - abs(t) ** 2 / N ** 2
+    grad = np.zeros(len(angles))
+    # group the op list into blocks (entangler + following rotations) walking backwards
+    i = len(ops) - 1
+    while i >= 0:
+        j = i
+        while j >= 0 and ops[j][0] in (RX, RY, RZ):
+            j -= 1
+        rots = ops[j + 1:i + 1]
+        ent = ops[j] if j >= 0 else None
+        # undo the rotations one by one (gradients of the individual angles), except that the SO(3)
+        # matrix of the FIRST rotation in time on each block qubit also carries Rz(a/2)
+        for kind, q0, q1, pi, const in reversed(rots):
+            a = angles[pi] if pi >= 0 else const
+            b = 1 << (n - 1 - q0)
+            if pi >= 0:
+                grad[pi] += {RX: h[b, 0], RY: h[b, b], RZ: h[0, b]}[kind]
+            h = conj_su2(h, so3_of(rot_mat(kind, a)).T, n - 1 - q0)
+        if ent is not None:
+            kind, q0, q1, pi, const = ent
+            a = (angles[pi] if pi >= 0 else const) if kind == CP else math.pi
+            for q in (q0, q1):
+                h = conj_su2(h, so3_of(rot_mat(RZ, a / 2)).T, n - 1 - q)
+            b1, b2 = 1 << (n - 1 - q0), 1 << (n - 1 - q1)
+            if kind == CP and pi >= 0:
+                grad[pi] += -0.5 * (h[0, 0] - h[0, b1] - h[0, b2] + h[0, b1 | b2])
+            h = conj_zz(h, a, n - 1 - q0, n - 1 - q1)
+        i = j - 1
+    return loss, grad
