@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--iters", type=int, default=2000, help="Adam iterations per step (num_gd_iterations)")
     ap.add_argument("--layer", default="chain", choices=["chain", "star"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-static", action="store_true", help="skip the Synthesize.static() wall-time extras")
     ap.add_argument("--cpu-samples", type=int, default=1024)
     ap.add_argument("--cpu-iters", type=int, default=30)
     return ap.parse_args()
@@ -213,6 +214,39 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def static_wall_times():
+    """Second half of BASELINE.json's metric: wall time of the whole Synthesize.static() call (sampling, the
+    fused Adam stage, selection, batched verification, result objects) on BASELINE configs[0] (README example,
+    'one to five minutes' on the reference's CPU path) and configs[1] (Toffoli-3, all-to-all, 10^4 samples)."""
+    import contextlib
+    import io
+    import numpy as np
+    import cpflow_b200 as cp
+    from cpflow_b200.gates import u_toff3
+    from cpflow_b200.topology import chain_layer, connected_layer
+    out = {}
+    ccz = np.diag([1, 1, 1, 1, 1, 1, 1, -1]).astype(complex)
+    cases = [("C1_ccz_chain_K12_B10", chain_layer(3), ccz,
+              dict(num_cp_gates=12, accepted_num_cz_gates=10, num_samples=10)),
+             ("C2_toffoli3_connected_K7_B10000", connected_layer(3), u_toff3,
+              dict(num_cp_gates=7, r=0.00131, accepted_num_cz_gates=6, num_samples=10000))]
+    for name, layer, target, kw in cases:
+        try:
+            syn = cp.Synthesize(layer, target_unitary=target, label=name)
+            opts = cp.StaticOptions(**kw)
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                syn.static(opts, save_results=False)          # warm-up (module import, allocator, device program)
+                t0 = time.perf_counter()
+                res = syn.static(opts, save_results=False)
+                dt = time.perf_counter() - t0
+            cz = sorted(d.cz_count for d in res.decompositions)
+            out[name] = {"wall_s": dt, "decompositions": len(cz), "min_cz": cz[0] if cz else None,
+                         "prospective": len(syn.last_prospective_cz_counts)}
+        except Exception as e:   # an extra must never take the headline down
+            out[name] = {"error": repr(e)}
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -360,6 +394,10 @@ def run_b200(args):
                "sample": f"{args.cpu_samples} samples x {args.cpu_iters} Adam iterations of the same C3 program "
                          f"(torch CPU oracle, complex64)", "host_cores": os.cpu_count()}
 
+    static_wall = None
+    if world == 1 and not args.no_static:
+        static_wall = static_wall_times()
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (complex64 amplitudes)", "data": "synthetic",
@@ -368,7 +406,7 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "cpflow_b200.optimization.mynimize_repeated(host arrays)", "timer": "wall clock"},
-            "gpu_launches": 2 * args.steps, "clocks": clocks}
+            "gpu_launches": 2 * args.steps, "clocks": clocks, "static_wall_s": static_wall}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
