@@ -16,13 +16,13 @@
 //             are N^2 REAL numbers: one xor-shuffle all-to-all gathers the x-diagonals (lane = x >> PB)
 //             and a register-local Walsh-Hadamard transform over r produces W.
 //   backward  H_{k-1} = G_k^dag H_k G_k acts on h by real linear maps: a fused one-qubit gate rotates
-//             (h_X, h_Y, h_Z) of its qubit with the transpose of its SO(3) matrix (2.25 FMA per
-//             coefficient when the qubit's x bit is a register bit, 4 FMA + 0.5 SHFL when it is a lane
-//             bit), a CP gate rotates two difference pairs per (z1, z2) quad (2.5 FMA per coefficient).
+//             (h_X, h_Y, h_Z) of its qubit with the transpose of its SO(3) matrix (packed over the register x bit:
+//             4 FFMA2 + 1 SHFL per pair when the qubit's x bit is a lane bit); CP(a) ~ Rz Rz exp(i a/4 ZZ): the Rz
+//             halves are folded into the SO(3) matrices, the ZZ part is a pair rotation by a/2.
 //             Every gradient entry is ONE coefficient of h (X: h[b,0], Y: h[b,b], Z: h[0,b]; CP:
 //             -(h[0,0]-h[0,b1]-h[0,b2]+h[0,b1|b2])/2): no reductions.
 //
-// Per sample and eval for C3 (n = 4, K = 40): ~300 k FMA-lane operations instead of ~680 k.
+// Per sample and eval for C3 (n = 4, K = 40): ~7.0 k warp instructions (x 1/4 warp) instead of ~22 k.
 #pragma once
 #include "engine_impl.cuh"
 
@@ -172,10 +172,6 @@ struct HeisSweep {
   // ------------------------------- backward: real maps on h -------------------------------
   // h[xr][z] is held packed over xr: hv[z] = (h[0][z], h[1][z]) for CPT = 2 (scalar for CPT = 1), so every map
   // whose coefficients do not depend on xr issues as FFMA2; only gates on amplitude bit 0 (x bit = xr) are scalar.
-  static __device__ __forceinline__ V selv(bool pr, V a, V b) {
-    if constexpr (CPT == 2) return T::make(pr ? a.x : b.x, pr ? a.y : b.y);
-    else return pr ? a : b;
-  }
   // Fused one-qubit gate on amplitude bit B.  cf: rows of M = R(G)^T, (X', Y', Z') = M (X, Y, Z), each row
   // padded to 4 words; the pad words 3 / 7 / 11 receive the gradient sums (S_X, S_Y, S_Z) = entries of h.
   template <int B>

@@ -58,7 +58,17 @@ class RawResults:
         return (self[i] for i in range(len(self)))
 
     def cpu(self):
-        return RawResults(self.params.cpu(), self.regloss.cpu(), self.reg.cpu())
+        """Device -> host through pinned staging buffers (torch caches pinned allocations), one synchronise."""
+        def to_host(t):
+            if not t.is_cuda:
+                return t
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+        out = [to_host(self.params), to_host(self.regloss), to_host(self.reg)]
+        if self.params.is_cuda:
+            torch.cuda.current_stream(self.params.device).synchronize()
+        return RawResults(*out)
 
     def numpy(self):
         r = self.cpu()
