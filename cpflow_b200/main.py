@@ -80,11 +80,13 @@ class Decomposition:
         """main.py:293-319 / exact_decompositions.py:293-344 (angle reduction and rationalisation on the
         forward-only engine; the Solovay-Kitaev / Clifford+T stage needs qiskit and is not provided)."""
         from .exact_decompositions import refine
-        qc, refine_type = refine(self.circuit, self.unitary_loss_func, max_denominator=max_denominator,
-                                 angle_threshold=angle_threshold, cp_threshold=cp_threshold,
-                                 reduce_threshold=reduce_threshold)
+        qc, refine_type, t_count, t_depth = refine(self.circuit, self.unitary_loss_func,
+                                                   max_denominator=max_denominator, angle_threshold=angle_threshold,
+                                                   cp_threshold=cp_threshold, reduce_threshold=reduce_threshold)
         self.type = refine_type
         self.circuit = qc
+        if refine_type == 'Clifford+T':
+            self.t_count, self.t_depth = t_count, t_depth
         return f'Refined to {refine_type}'
 
     def __repr__(self):

@@ -785,3 +785,36 @@ def generate_initial_angles(seed, num_angles, cp_mask, cp_dist="uniform", batch_
 def next_adaptive_seed(seed):
     """main.py:798-799: `_, subkey = split(PRNGKey(seed)); seed = int(subkey[1])`."""
     return int(prng_split(prng_key(seed), 2)[1][1])
+
+
+# --------------------------------------------------------------------------------------
+# refine path (SURVEY.md §8a row R2): exact_decompositions.py:77-113, sequential restatement
+# --------------------------------------------------------------------------------------
+
+
+def reduce_all_1q_angles(loss_func, initial_angles, wires, threshold=1e-5):
+    """exact_decompositions.py:77-113 unrolled into a loop: angle k (earlier ones already final) is set to zero
+    if the loss stays below `threshold`, else merged into the first later angle on the same wire for which
+    a_i -/+ a_k passes (sign -1 tried first)."""
+    angles = np.array(initial_angles, dtype=np.float64)
+    G = len(angles)
+    for k in range(G):
+        trial = angles.copy()
+        trial[k] = 0.0
+        if loss_func(trial) < threshold:                       # reduce_first_1q_angle, :90-92
+            angles = trial
+            continue
+        done = False
+        for i in range(k + 1, G):                               # :95-98
+            if wires[i] != wires[k]:                            # can_reduce_two_angles, :104-105
+                continue
+            for sign in (-1, 1):                                # :107-113
+                trial = angles.copy()
+                trial[i] = angles[i] + sign * angles[k]
+                trial[k] = 0.0
+                if loss_func(trial) < threshold:
+                    angles, done = trial, True
+                    break
+            if done:
+                break
+    return angles
