@@ -6,7 +6,7 @@ loop on BASELINE.json's metric configuration (4-qubit Toffoli, 40 CP gates, comp
     python bench.py --impl reference --steps K --warmup W    # CPU arm (oracle port of cpflow)
 
 A *step* is one complete stage-1 run of `Synthesize.static()` for this rank's shard of samples:
-B = 12 500 independent random initialisations (10^5 over 8 GPUs, BASELINE configs[2]) x T = 2000
+B = 10^5 independent random initialisations (the sample count of BASELINE configs[2]) x T = 2000
 Adam iterations, every iteration = forward sweep + loss + penalty + adjoint sweep + Adam update +
 best tracking, all inside ONE launch of the fused engine kernel.  One "eval" = one such iteration
 of one sample.  Samples shard over ranks with no data-path collective ("weak" scaling: per-GPU
@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--samples-per-gpu", type=int, default=12500)
+    # C3 quotes 10^5 samples: at N = 1 the whole configuration runs on one GPU; N > 1 keeps the per-GPU work (weak)
+    ap.add_argument("--samples-per-gpu", type=int, default=100000)
     ap.add_argument("--iters", type=int, default=2000, help="Adam iterations per step (num_gd_iterations)")
     ap.add_argument("--layer", default="chain", choices=["chain", "star"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -43,11 +43,18 @@ template <> struct Vec4Load<float> {
   static __device__ __forceinline__ void ld(const float* p, float& a, float& b, float& c, float& d) {
     float4 t = *reinterpret_cast<const float4*>(p); a = t.x; b = t.y; c = t.z; d = t.w;
   }
+  static __device__ __forceinline__ void st(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+  }
 };
 template <> struct Vec4Load<double> {
   static __device__ __forceinline__ void ld(const double* p, double& a, double& b, double& c, double& d) {
     double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 2);
     a = t.x; b = t.y; c = u.x; d = u.y;
+  }
+  static __device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
   }
 };
 

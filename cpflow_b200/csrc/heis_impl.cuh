@@ -28,11 +28,18 @@
 
 namespace cpf {
 
-constexpr int HEIS_SU2_WORDS = 12;   // alpha,beta (fwd) -> M rows padded to float4 (bwd); pads 3,7,11 = S
+// Shared-memory slot of a fused one-qubit gate, 8 words: cy, sy | u_out | u_in (surface) / A (lower-qubit gate) /
+// A B e^{ia} (higher-qubit gate) | B (lower-qubit gate).  The backward sweep overwrites words 0..2 with the
+// gradient sums (S_X, S_Y, S_Z).  The SO(3) rows of the backward sweep are NOT kept per gate: they are
+// produced one layer at a time in a staging area (HEIS_STAGE_WORDS per gate of a layer), which keeps the
+// per-sample footprint small enough for two co-resident CTAs of 7-8 warps per SM.
+constexpr int HEIS_SU2_WORDS = 8;
+constexpr int HEIS_STAGE_WORDS = 12; // rows of M = R(G)^T padded to 4 words
+constexpr int HEIS_SKEW_DEFAULT = 0;    // % of a CTA's warps in phase group A (heis_kernel); 0 = unskewed
 constexpr int HEIS_CP_WORDS = 4;     // cos(a/2), sin(a/2), r * penalty slope, - ; word 0 <- dL/da after the backward sweep
 
-inline int heis_coef_stride(int n_su2, int n_cp) {
-  int w = (HEIS_SU2_WORDS * n_su2 + HEIS_CP_WORDS * n_cp + 3) & ~3;
+inline int heis_coef_stride(int n_su2, int n_cp, int n_stage) {
+  int w = (HEIS_SU2_WORDS * n_su2 + HEIS_CP_WORDS * n_cp + HEIS_STAGE_WORDS * n_stage + 3) & ~3;
   if (w == 0) w = 4;
   if (((w / 4) & 1) == 0) w += 4;   // odd number of 16-byte groups: samples of a warp hit distinct banks
   return w;
@@ -49,9 +56,23 @@ struct HCfg {
   static constexpr int XR = 1 << PB;
   static constexpr int TPS = N / CPT;           // threads per sample
   // forward state registers: 2 * N * CPT words (x2 for double) -> register cap 168 (384 threads) or 255
-  static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? 384 : 256;
+  static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? 512 : 256;
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
 };
+
+// Barrier that keeps the warps of one phase group on the same instruction-cache lines.  Unskewed launch:
+// id 0 over the whole CTA (== __syncthreads()); skewed launch (heis_kernel): one named barrier per group.
+struct LayerBar {
+  int id, cnt;
+  __device__ __forceinline__ void sync() const {   // immediate ids: a register id makes ptxas reserve all 16 barriers
+    if (id == 0) asm volatile("bar.sync 0, %0;" ::"r"(cnt) : "memory");
+    else if (id == 1) asm volatile("bar.sync 1, %0;" ::"r"(cnt) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"r"(cnt) : "memory");
+  }
+};
+
+// CTA-wide barrier reached from different code positions by the two phase groups (plain bar.sync 0)
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 template <typename V> struct AddV;
 template <> struct AddV<float> { static __device__ __forceinline__ float add(float a, float b) { return a + b; }
@@ -72,7 +93,8 @@ struct HeisSweep {
   using T = VT<R, CPT>;
   using V = typename T::V;
   static constexpr int N = 1 << NQ, PB = CPT == 2 ? 1 : 0, XR = 1 << PB, TPS = N / CPT;
-  static constexpr int SW = HEIS_SU2_WORDS, CW = HEIS_CP_WORDS;
+  static constexpr int SW = HEIS_SU2_WORDS, CW = HEIS_CP_WORDS, STW = HEIS_STAGE_WORDS;
+  static constexpr int NSTAGE = 2 * NBL > NQ ? 2 * NBL : NQ;   // gates staged at a time (one layer / the surface)
   static __host__ __device__ constexpr int lo_q(int j) { return (int)((LOQ >> (4 * j)) & 15); }
   static __host__ __device__ constexpr int hi_q(int j) { return (int)((HIQ >> (4 * j)) & 15); }
 
@@ -81,17 +103,17 @@ struct HeisSweep {
   // loss and the Hermitian part that seeds the backward sweep do not see it).  u_in merges with the block's
   // CP phase and with the u_out still pending on the same qubits into one diagonal (1, B, A, A B e^{ia}),
   // prepared by the parameter phase: a block costs 3 + 4 + 4 = 11 FMA per amplitude instead of 1 + 8 + 8.
-  // Slot words during the forward sweep: [0,4) alpha, beta; 4 cy; 5 sy; [6,8) u_out; lower-qubit slot
-  // [8,12) A, B; higher-qubit slot [8,10) A B e^{ia}; surface slots [8,10) u_in.
+  // Slot words during the forward sweep: 0 cy; 1 sy; [2,4) u_out; lower-qubit slot [4,8) A, B;
+  // higher-qubit slot [4,6) A B e^{ia}; surface slots [4,6) u_in.
   template <int BP>
   static __device__ __forceinline__ void ry_fwd(V (&yr)[N], V (&yi)[N], const R* cf) {
-    CO::template ry_reg<BP>(yr, yi, cf[4], cf[5]);
+    CO::template ry_reg<BP>(yr, yi, cf[0], cf[1]);
   }
   template <int Q>
   static __device__ __forceinline__ void surface_fwd(V (&yr)[N], V (&yi)[N], const R* coef) {
     if constexpr (Q < NQ) {
       constexpr int BP = NQ - 1 - Q;
-      CO::template phase_mask<(1 << BP), 0>(yr, yi, coef[SW * Q + 8], coef[SW * Q + 9]);
+      CO::template phase_mask<(1 << BP), 0>(yr, yi, coef[SW * Q + 4], coef[SW * Q + 5]);
       ry_fwd<BP>(yr, yi, coef + SW * Q);
       surface_fwd<Q + 1>(yr, yi, coef);
     }
@@ -100,7 +122,7 @@ struct HeisSweep {
   static __device__ __forceinline__ void tail_fwd(const KParams<R>& p, V (&yr)[N], V (&yi)[N], const R* coef) {
     if constexpr (Q < NQ) {
       const R* cf = coef + SW * p.last_slot[Q];
-      CO::template phase_mask<(1 << (NQ - 1 - Q)), 0>(yr, yi, cf[6], cf[7]);
+      CO::template phase_mask<(1 << (NQ - 1 - Q)), 0>(yr, yi, cf[2], cf[3]);
       tail_fwd<Q + 1>(p, yr, yi, coef);
     }
   }
@@ -112,22 +134,23 @@ struct HeisSweep {
       const R* cl = cs + 2 * SW * J;
       const R* ch = cl + SW;
       R ar, ai, br, bi;
-      Vec4Load<R>::ld(cl + 8, ar, ai, br, bi);
+      Vec4Load<R>::ld(cl + 4, ar, ai, br, bi);
       CO::template phase_mask<(1 << PA), (1 << PC)>(yr, yi, ar, ai);
       CO::template phase_mask<(1 << PC), (1 << PA)>(yr, yi, br, bi);
-      CO::template phase_mask<(1 << PA) | (1 << PC), 0>(yr, yi, ch[8], ch[9]);
+      CO::template phase_mask<(1 << PA) | (1 << PC), 0>(yr, yi, ch[4], ch[5]);
       ry_fwd<PA>(yr, yi, cl);
       ry_fwd<PC>(yr, yi, ch);
       blocks_fwd<J + 1>(k0, K, cs, yr, yi);
     }
   }
-  static __device__ __forceinline__ void forward(const KParams<R>& p, const R* coef, V (&yr)[N], V (&yi)[N]) {
+  static __device__ __forceinline__ void forward(const KParams<R>& p, const LayerBar lb, const R* coef, V (&yr)[N],
+                                                 V (&yi)[N]) {
     surface_fwd<0>(yr, yi, coef);
     const int K = p.n_cp;
     const R* cs = coef + SW * NQ;
 #pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += NBL) {
-      __syncthreads();   // keep the warps of the CTA on the same instruction-cache lines
+      lb.sync();   // keep the warps of the group on the same instruction-cache lines
       blocks_fwd<0>(k0, K, cs, yr, yi);
       cs += 2 * SW * NBL;
     }
@@ -172,16 +195,16 @@ struct HeisSweep {
   // ------------------------------- backward: real maps on h -------------------------------
   // h[xr][z] is held packed over xr: hv[z] = (h[0][z], h[1][z]) for CPT = 2 (scalar for CPT = 1), so every map
   // whose coefficients do not depend on xr issues as FFMA2; only gates on amplitude bit 0 (x bit = xr) are scalar.
-  // Fused one-qubit gate on amplitude bit B.  cf: rows of M = R(G)^T, (X', Y', Z') = M (X, Y, Z), each row
-  // padded to 4 words; the pad words 3 / 7 / 11 receive the gradient sums (S_X, S_Y, S_Z) = entries of h.
+  // Fused one-qubit gate on amplitude bit B.  cf: rows of M = R(G)^T in the staging area, (X', Y', Z') = M (X, Y, Z),
+  // each row padded to 4 words; words 0..2 of the gate's slot receive the gradient sums (S_X, S_Y, S_Z) = entries of h.
   template <int B>
-  static __device__ __forceinline__ void su2_bwd(V (&hv)[N], R* cf, int m) {
+  static __device__ __forceinline__ void su2_bwd(V (&hv)[N], const R* cf, R* sl, int m) {
     constexpr int BM = 1 << B;
     if constexpr (B < PB) {
-      if (m == 0) { cf[3] = T::get(hv[0], 1); cf[7] = T::get(hv[BM], 1); cf[11] = T::get(hv[BM], 0); }
+      if (m == 0) { sl[0] = T::get(hv[0], 1); sl[1] = T::get(hv[BM], 1); sl[2] = T::get(hv[BM], 0); }
     } else {
-      if (m == (1 << (B - PB))) { cf[3] = T::get(hv[0], 0); cf[7] = T::get(hv[BM], 0); }
-      if (m == 0) cf[11] = T::get(hv[BM], 0);
+      if (m == (1 << (B - PB))) { sl[0] = T::get(hv[0], 0); sl[1] = T::get(hv[BM], 0); }
+      if (m == 0) sl[2] = T::get(hv[BM], 0);
     }
     R m00, m01, m02, m10, m11, m12, m20, m21, m22, pad;
     Vec4Load<R>::ld(cf, m00, m01, m02, pad);
@@ -274,50 +297,77 @@ struct HeisSweep {
   }
 
   template <int J>
-  static __device__ __forceinline__ void blocks_bwd(int k0, int K, R* cs, R* cph, int m, V (&h)[N]) {
+  static __device__ __forceinline__ void blocks_bwd(int k0, int K, R* cs, const R* stage, R* cph, int m, V (&h)[N]) {
     if constexpr (J >= 0) {
       if (k0 + J < K) {
         constexpr int PA = NQ - 1 - lo_q(J), PC = NQ - 1 - hi_q(J);
-        su2_bwd<PC>(h, cs + 2 * SW * J + SW, m);
-        su2_bwd<PA>(h, cs + 2 * SW * J, m);
+        su2_bwd<PC>(h, stage + STW * (2 * J + 1), cs + 2 * SW * J + SW, m);
+        su2_bwd<PA>(h, stage + STW * (2 * J), cs + 2 * SW * J, m);
         phase_bwd<PA, PC>(h, cph + CW * J, m);
       }
-      blocks_bwd<J - 1>(k0, K, cs, cph, m, h);
+      blocks_bwd<J - 1>(k0, K, cs, stage, cph, m, h);
     }
   }
   template <int Q>
-  static __device__ __forceinline__ void surface_bwd(R* coef, int m, V (&h)[N]) {
+  static __device__ __forceinline__ void surface_bwd(R* coef, const R* stage, int m, V (&h)[N]) {
     if constexpr (Q >= 0) {
-      su2_bwd<NQ - 1 - Q>(h, coef + SW * Q, m);
-      surface_bwd<Q - 1>(coef, m, h);
+      su2_bwd<NQ - 1 - Q>(h, stage + STW * Q, coef + SW * Q, m);
+      surface_bwd<Q - 1>(coef, stage, m, h);
     }
   }
-  static __device__ __forceinline__ void backward(const KParams<R>& p, R* coef, int m, V (&h)[N]) {
+  // SO(3) rows of G' = diag(1, u_out) Ry diag(1, u_in') = Rz3(phi_out) Ry3(theta) Rz3(phi_in'), stored transposed
+  // (M = R^T) in rows of 4 words.  (ci, si) = u_in' = u_in e^{i a/2} carries the block's share of its CP gate.
+  static __device__ __forceinline__ void zyz_to_so3(R* st, R cy, R sy, R co, R so, R ci, R si) {
+    const R ct = cy * cy - sy * sy, sth = R(2) * cy * sy;
+    const R cc = ct * ci, cs2 = ct * si;
+    Vec4Load<R>::st(st, co * cc - so * si, so * cc + co * si, -sth * ci, R(0));
+    Vec4Load<R>::st(st + 4, -(co * cs2 + so * ci), co * ci - so * cs2, sth * si, R(0));
+    Vec4Load<R>::st(st + 8, co * sth, so * sth, ct, R(0));
+  }
+  // Staging of one layer (blocks k0 .. k0 + NBL - 1): the sample's lanes split the layer's 2 NBL fused gates.
+  // u_in of a block gate is recovered from the merged diagonal: u_in = A conj(pending u_out of the previous gate).
+  static __device__ __forceinline__ void stage_layer(const KParams<R>& p, int k0, int K, const R* coef, const R* cph0,
+                                                     R* stage, int m) {
+    const int nb = K - k0 < NBL ? K - k0 : NBL;
+#pragma unroll 1
+    for (int j = m; j < 2 * nb; j += TPS) {
+      const int k = k0 + (j >> 1), hi = j & 1;
+      const CpMeta* md = p.cp + k;
+      const R* cl = coef + SW * (NQ + 2 * k);
+      const R* cf = cl + SW * hi;
+      const R* pv = coef + SW * (hi ? md->prev_hi : md->prev_lo);
+      const R* cc = cph0 + CW * k;
+      const R dr = cl[4 + 2 * hi], di = cl[5 + 2 * hi];          // A (lower-qubit gate) / B (higher-qubit gate)
+      const R pr = pv[2], pi = pv[3];
+      const R ur = dr * pr + di * pi, ui = di * pr - dr * pi;    // u_in = d conj(pend)
+      const R ch = cc[0], sh = cc[1];
+      zyz_to_so3(stage + STW * j, cf[0], cf[1], cf[2], cf[3], ur * ch - ui * sh, ur * sh + ui * ch);
+    }
+  }
+  static __device__ __forceinline__ void stage_surface(const R* coef, R* stage, int m) {
+#pragma unroll 1
+    for (int q = m; q < NQ; q += TPS) {
+      const R* cf = coef + SW * q;
+      zyz_to_so3(stage + STW * q, cf[0], cf[1], cf[2], cf[3], cf[4], cf[5]);
+    }
+  }
+  static __device__ __forceinline__ void backward(const KParams<R>& p, const LayerBar lb, R* coef, R* stage, int m,
+                                                  V (&h)[N]) {
     const int K = p.n_cp;
     R* cph0 = coef + SW * p.n_su2;
 #pragma unroll 1
     for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL) {
-      __syncthreads();
-      blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, cph0 + CW * k0, m, h);
+      lb.sync();
+      stage_layer(p, k0, K, coef, cph0, stage, m);
+      __syncwarp();
+      blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
+      __syncwarp();
     }
-    surface_bwd<NQ - 1>(coef, m, h);
+    stage_surface(coef, stage, m);
+    __syncwarp();
+    surface_bwd<NQ - 1>(coef, stage, m, h);
   }
 };
-
-// SO(3) matrix of G = [[alpha, -conj(beta)], [beta, conj(alpha)]] = w - i (x sx + y sy + z sz), stored
-// transposed (M = R^T) in rows of 4 words; the pad words are left alone (they carry the gradient sums).
-template <typename R>
-__device__ __forceinline__ void heis_su2_to_so3(R* cf, R ch, R sh) {
-  const R w = cf[0], z = -cf[1], y = cf[2], x = -cf[3];
-  const R xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
-  // rows of M = R(G)^T
-  const R x0 = R(1) - R(2) * (yy + zz), x1 = R(2) * (xy + wz), x2 = R(2) * (xz - wy);
-  const R y0 = R(2) * (xy - wz), y1 = R(1) - R(2) * (xx + zz), y2 = R(2) * (yz + wx);
-  // G' = G Rz(a/2) (the block's share of its CP gate, applied before G): M' = Rz3(-a/2) M mixes rows X and Y
-  cf[0] = ch * x0 + sh * y0; cf[1] = ch * x1 + sh * y1; cf[2] = ch * x2 + sh * y2;
-  cf[4] = ch * y0 - sh * x0; cf[5] = ch * y1 - sh * x1; cf[6] = ch * y2 - sh * x2;
-  cf[8] = R(2) * (xz + wy); cf[9] = R(2) * (yz - wx); cf[10] = R(1) - R(2) * (xx + yy);
-}
 
 // ------------------------------------------------------------------------------------------
 // update / coefficient phase helpers (per gate, executed by the gate's owner thread)
@@ -452,7 +502,7 @@ __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const U
   if (in.pi1 >= 0) in.v1 = pk_load(pk + in.pi1); else in.v1.th = R(md->cangle[1]);
   if (in.pi2 >= 0) in.v2 = pk_load(pk + in.pi2); else in.v2.th = R(md->cangle[2]);
   if (u.phase != PH_COEF) {
-    in.sx = cf[3]; in.sy = cf[7]; in.sz = cf[11];
+    in.sx = cf[0]; in.sy = cf[1]; in.sz = cf[2];
     Vec4Load<R>::ld(ax, in.c2, in.s2, in.c3, in.s3);
   }
   return in;
@@ -490,16 +540,15 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
     su2_of(ax0, c0, s0, ar, ai, br, bi);
     su2_lmul_axis(ax1, c1, s1, ar, ai, br, bi);
     su2_lmul_axis(ax2, c2, s2, ar, ai, br, bi);
-    cf[0] = ar; cf[1] = ai; cf[2] = br; cf[3] = bi;
     if (u.active) { ax[0] = c1; ax[1] = s1; ax[2] = c2; ax[3] = s2; }
     // ZYZ form for the forward sweep: alpha = cy p_a, beta = sy p_b, u_out = p_b conj(p_a), u_in = conj(p_a p_b)
     const R na = ar * ar + ai * ai, nb = br * br + bi * bi;
     const bool oka = na > R(1e-30), okb = nb > R(1e-30);
     const R ia = oka ? rsqrt_r(na) : R(0), ib = okb ? rsqrt_r(nb) : R(0);
     const R par = oka ? ar * ia : R(1), pai = ai * ia, pbr = okb ? br * ib : R(1), pbi = bi * ib;
-    cf[4] = na * ia; cf[5] = nb * ib;
-    cf[6] = pbr * par + pbi * pai; cf[7] = pbi * par - pbr * pai;
-    cf[8] = par * pbr - pai * pbi; cf[9] = -(par * pbi + pai * pbr);
+    cf[0] = na * ia; cf[1] = nb * ib;
+    cf[2] = pbr * par + pbi * pai; cf[3] = pbi * par - pbr * pai;
+    cf[4] = par * pbr - pai * pbi; cf[5] = -(par * pbi + pai * pbr);
   }
 }
 // packed axes of a gate class: a0 | a1 << 4 | a2 << 8 (15 = unused slot); 0xffff = not uniform
@@ -589,6 +638,17 @@ heis_kernel(const KParams<R> p) {
   }
   const R NN = R(N) * R(N);
 
+  // Phase skew (M_ADAM launches with p.skew_split > 0): the warps of the CTA form two groups that run half a
+  // step apart, so the latency-bound parameter phase of one group overlaps the FMA-bound sweeps of the other.
+  // Half steps are separated by CTA-wide barriers (group B starts with one extra, group A ends with one extra);
+  // inside a sweep every group keeps its own per-layer barrier.
+  const bool skew = p.skew_split > 0;
+  const bool grp_b = skew && tid >= p.skew_split;
+  LayerBar lb;
+  lb.id = skew ? (grp_b ? 2 : 1) : 0;
+  lb.cnt = skew ? (grp_b ? (int)blockDim.x - p.skew_split : p.skew_split) : (int)blockDim.x;
+  if (grp_b) cta_sync();
+
   R best = R(0), best_reg_v = R(0);
   bool improved_prev = false;
   if (p.mode == M_ADAM && p.step0 > 0) { best = p.best_regloss[b]; best_reg_v = p.best_reg[b]; }
@@ -650,21 +710,22 @@ heis_kernel(const KParams<R> p) {
       const R* pl = coef + SW * md->prev_lo;
       const R* ph = coef + SW * md->prev_hi;
       const R* cc = coef_cp + CW * k;
-      const R plr = pl[6], pli = pl[7], phr = ph[6], phi = ph[7];
-      const R ar = plr * cl[8] - pli * cl[9], ai = plr * cl[9] + pli * cl[8];
-      const R br = phr * ch[8] - phi * ch[9], bi = phr * ch[9] + phi * ch[8];
+      const R plr = pl[2], pli = pl[3], phr = ph[2], phi = ph[3];
+      const R ar = plr * cl[4] - pli * cl[5], ai = plr * cl[5] + pli * cl[4];
+      const R br = phr * ch[4] - phi * ch[5], bi = phr * ch[5] + phi * ch[4];
       const R abr = ar * br - ai * bi, abi = ar * bi + ai * br;
       const R c = cc[0] * cc[0] - cc[1] * cc[1], s = R(2) * cc[0] * cc[1];   // e^{ia} from the half angle
-      cl[8] = ar; cl[9] = ai; cl[10] = br; cl[11] = bi;
-      ch[8] = abr * c - abi * s; ch[9] = abr * s + abi * c;
+      cl[4] = ar; cl[5] = ai; cl[6] = br; cl[7] = bi;
+      ch[4] = abr * c - abi * s; ch[5] = abr * s + abi * c;
     }
     __syncwarp();
 
+    if (skew) cta_sync();
     // ---------------- forward sweep: Y = U V^dag ----------------
     V yr[N], yi[N];
 #pragma unroll
     for (int r = 0; r < N; ++r) { yr[r] = tv[2 * r]; yi[r] = tv[2 * r + 1]; }
-    SWP::forward(p, coef, yr, yi);
+    SWP::forward(p, lb, coef, yr, yi);
 
     // ---------------- pivot to the Pauli basis ----------------
     SWP::gather_wht(yr, yi);
@@ -717,18 +778,14 @@ heis_kernel(const KParams<R> p) {
         h[z] = T::make(hc[0], hc[XR - 1]);
       }
     }
-    // fused-gate coefficients (alpha, beta) -> SO(3) rows, in place (the forward sweep is done with them)
-    __syncwarp();
-    for (int g = m; g < p.n_su2; g += TPS) {
-      const R* cc = coef_cp + CW * ((g - NQ) >> 1);      // block gates carry half of their CP gate's Rz
-      heis_su2_to_so3(coef + SW * g, g >= NQ ? cc[0] : R(1), g >= NQ ? cc[1] : R(0));
-    }
     __syncwarp();
 
     // ---------------- Heisenberg sweep ----------------
-    SWP::backward(p, coef, m, h);
+    SWP::backward(p, lb, coef, coef_cp + CW * p.n_cp, m, h);
     __syncwarp();
+    if (skew) cta_sync();
   }
+  if (skew && !grp_b) cta_sync();
 
   if (p.mode == M_ADAM && active) {
     // unpack the optimiser state into the caller's arrays
@@ -792,9 +849,22 @@ template <typename R, int NQ, int CPT, typename SWP>
 int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   using C = HCfg<R, NQ, CPT>;
   p.n_sched = 0; p.n_red = 0;
-  p.coef_stride = heis_coef_stride(p.n_su2, p.n_cp);
+  p.coef_stride = heis_coef_stride(p.n_su2, p.n_cp, SWP::NSTAGE);
   const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes, (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT);
   p.spb = g.spb;
+  // phase skew: env CPF_HEIS_SKEW = percentage of the CTA's warps in group A (0 = off)
+  p.skew_split = 0;
+  {
+    int pct = HEIS_SKEW_DEFAULT;
+    if (const char* e = getenv("CPF_HEIS_SKEW")) { int v = atoi(e); if (v >= 0 && v < 100) pct = v; }
+    const int warps = g.block / 32;
+    if (p.mode == M_ADAM && pct > 0 && warps >= 2) {
+      int wa = (warps * pct + 50) / 100;
+      if (wa < 1) wa = 1;
+      if (wa > warps - 1) wa = warps - 1;
+      p.skew_split = wa * 32;
+    }
+  }
   if (g.smem > 227 * 1024) {
     err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
     return CPF_ERR_UNSUPPORTED;
