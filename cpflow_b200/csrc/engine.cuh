@@ -62,6 +62,7 @@ struct KParams {
   R* aux;           // heis_kernel: [B][n_su2][4] half-angle cos/sin of the 2nd and 3rd fused rotations
   int coef_stride;  // R words per sample in shared memory
   int spb;          // heis_kernel: sample slots used per CTA
+  int sync_every, sync_every_bwd;   // heis_kernel: CTA barrier at every n-th layer of the forward / backward sweep
   int skew_split;   // heis_kernel: threads in phase group A (multiple of 32); 0 = all warps in phase
   int colmode;      // engine_kernel<SINGLE>, M_UNITARY: virtual sample b = (sample b / N, column b % N)
   int axp_surface, axp_block;   // heis_kernel: packed rotation axes shared by the surface / block gates
@@ -199,6 +200,35 @@ __device__ __forceinline__ void penalty_eval(const PenaltyT<R>& pen, R a, R& val
         break;
       }
     }
+  } else if (pen.kind == CPF_PEN_L1) {
+    val = abs_r(a);
+    slope = a > R(0) ? R(1) : (a < R(0) ? R(-1) : R(0));
+  }
+}
+
+// Same values as penalty_eval, shaped for the per-gate loops of heis_kernel: the common ranges of jnp.mod are
+// handled inline (a in [0, p): a; [p, 2p): a - p exactly; (-p, 0): a + p rounded once, as the fmod route does),
+// and the first-true-wins search over the (disjoint) segments runs branch-free from the last segment down.
+template <typename R>
+__device__ __forceinline__ void penalty_eval_fast(const PenaltyT<R>& pen, R a, R& val, R& slope) {
+  val = R(0); slope = R(0);
+  if (pen.kind == CPF_PEN_PIECEWISE) {
+    const R per = pen.period;
+    R am;
+    if (a >= R(0) && a < per) am = a;
+    else if (a >= per && a < per + per) am = a - per;
+    else if (a < R(0) && a > -per) am = add_rn(a, per);
+    else am = pymod(a, per);
+    R sl = R(0), ic = R(0);
+    bool found = false;
+#pragma unroll
+    for (int s = CPF_MAX_SEGMENTS - 1; s >= 0; --s) {
+      const bool in = s < pen.nseg && pen.lo[s] < am && am <= pen.hi[s];
+      sl = in ? pen.slope[s] : sl;
+      ic = in ? pen.icpt[s] : ic;
+      found = found || in;
+    }
+    if (found) { val = add_rn(mul_rn(sl, am), ic); slope = sl; }
   } else if (pen.kind == CPF_PEN_L1) {
     val = abs_r(a);
     slope = a > R(0) ? R(1) : (a < R(0) ? R(-1) : R(0));

@@ -35,6 +35,7 @@ namespace cpf {
 // per-sample footprint small enough for two co-resident CTAs of 7-8 warps per SM.
 constexpr int HEIS_SU2_WORDS = 8;
 constexpr int HEIS_STAGE_WORDS = 12; // rows of M = R(G)^T padded to 4 words
+constexpr int HEIS_SYNC_EVERY_DEFAULT = 1 << 20;   // layers between CTA barriers inside a sweep (first layer always)
 constexpr int HEIS_SKEW_DEFAULT = 0;    // % of a CTA's warps in phase group A (heis_kernel); 0 = unskewed
 constexpr int HEIS_CP_WORDS = 4;     // cos(a/2), sin(a/2), r * penalty slope, - ; word 0 <- dL/da after the backward sweep
 
@@ -63,7 +64,7 @@ struct HCfg {
 // Barrier that keeps the warps of one phase group on the same instruction-cache lines.  Unskewed launch:
 // id 0 over the whole CTA (== __syncthreads()); skewed launch (heis_kernel): one named barrier per group.
 struct LayerBar {
-  int id, cnt;
+  int id, cnt, every, every_bwd;   // barrier at every `every`-th layer of the forward / backward sweep (0 = never)
   __device__ __forceinline__ void sync() const {   // immediate ids: a register id makes ptxas reserve all 16 barriers
     if (id == 0) asm volatile("bar.sync 0, %0;" ::"r"(cnt) : "memory");
     else if (id == 1) asm volatile("bar.sync 1, %0;" ::"r"(cnt) : "memory");
@@ -149,8 +150,10 @@ struct HeisSweep {
     const int K = p.n_cp;
     const R* cs = coef + SW * NQ;
 #pragma unroll 1
+    int li = 0;
     for (int k0 = 0; k0 < K; k0 += NBL) {
-      lb.sync();   // keep the warps of the group on the same instruction-cache lines
+      if (li == 0 && lb.every > 0) lb.sync();   // keep the warps of the group on the same instruction-cache lines
+      li = li + 1 == lb.every ? 0 : li + 1;
       blocks_fwd<0>(k0, K, cs, yr, yi);
       cs += 2 * SW * NBL;
     }
@@ -356,8 +359,10 @@ struct HeisSweep {
     const int K = p.n_cp;
     R* cph0 = coef + SW * p.n_su2;
 #pragma unroll 1
+    int li = 0;
     for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL) {
-      lb.sync();
+      if (li == 0 && lb.every_bwd > 0) lb.sync();
+      li = li + 1 == lb.every_bwd ? 0 : li + 1;
       stage_layer(p, k0, K, coef, cph0, stage, m);
       __syncwarp();
       blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
@@ -406,9 +411,11 @@ __device__ __forceinline__ void pk_store(Pk4<double>* q, const Pk4<double>& v) {
   reinterpret_cast<double2*>(q)[1] = make_double2(v.nu, v.best);
 }
 
+__device__ __forceinline__ float rsqrt_fast(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ double rsqrt_fast(double a) { return rsqrt_r(a); }
 static __device__ __noinline__ SinCos<float> sincos_slow_v(float x) { float s, c; sincosf(x, &s, &c); return {s, c}; }
 // sin/cos for the parameter phase, inlined so the three evaluations of a fused gate interleave
-__device__ __forceinline__ void sincos_inl(float x, float& s, float& c) {
+__device__ __forceinline__ void sincos_core(float x, float& s, float& c) {
   const float j = rintf(x * 0.636619747f);
   float r = fmaf(j, -1.57079601e+00f, x);
   r = fmaf(j, -3.13916473e-07f, r);
@@ -425,9 +432,30 @@ __device__ __forceinline__ void sincos_inl(float x, float& s, float& c) {
   const float cc = (q & 1) ? sp : cp;
   s = (q & 2) ? -ss : ss;
   c = ((q + 1) & 2) ? -cc : cc;
+}
+__device__ __forceinline__ void sincos_inl(float x, float& s, float& c) {
+  sincos_core(x, s, c);
   if (fabsf(x) > 48000.f) { const SinCos<float> t = sincos_slow_v(x); s = t.s; c = t.c; }
 }
 __device__ __forceinline__ void sincos_inl(double x, double& s, double& c) { sincos_r(x, s, c); }
+// the three half angles of a fused gate: one (never taken in practice) large-argument test for all of them
+__device__ __forceinline__ void sincos3(bool on0, bool on1, bool on2, float x0, float x1, float x2, float& s0, float& c0,
+                                        float& s1, float& c1, float& s2, float& c2) {
+  if (on0) sincos_core(x0, s0, c0);
+  if (on1) sincos_core(x1, s1, c1);
+  if (on2) sincos_core(x2, s2, c2);
+  if (fmaxf(fmaxf(on0 ? fabsf(x0) : 0.f, on1 ? fabsf(x1) : 0.f), on2 ? fabsf(x2) : 0.f) > 48000.f) {
+    if (on0) sincos_inl(x0, s0, c0);
+    if (on1) sincos_inl(x1, s1, c1);
+    if (on2) sincos_inl(x2, s2, c2);
+  }
+}
+__device__ __forceinline__ void sincos3(bool on0, bool on1, bool on2, double x0, double x1, double x2, double& s0,
+                                        double& c0, double& s1, double& c1, double& s2, double& c2) {
+  if (on0) sincos_r(x0, s0, c0);
+  if (on1) sincos_r(x1, s1, c1);
+  if (on2) sincos_r(x2, s2, c2);
+}
 
 // optax scale_by_adam + scale(-lr) (optimization.py:22-23).  double: exact IEEE sequence of the oracle.
 // float: reciprocal bias corrections, approximate sqrt and division (<= 2 ulp each; the reference's XLA
@@ -444,24 +472,29 @@ __device__ __forceinline__ void adam_inl(const KParams<float>& p, const UpdCtx<f
   mu = add_rn(mul_rn(p.omb1, g), mul_rn(p.b1, mu));
   nu = add_rn(mul_rn(p.omb2, mul_rn(g, g)), mul_rn(p.b2, nu));
   const float mu_hat = mu * u.ibc1, nu_hat = nu * u.ibc2;
-  float rt;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(rt) : "f"(nu_hat));
-  th = add_rn(th, mul_rn(-p.lr, __fdividef(mu_hat, add_rn(rt, p.eps))));
+  // .ftz forms: without them ptxas wraps each MUFU in a denormal rescue (4 extra instructions); a denormal
+  // nu_hat is far below eps^2 either way
+  float rt, iv;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(nu_hat));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iv) : "f"(add_rn(rt, p.eps)));
+  th = add_rn(th, mul_rn(-p.lr, mul_rn(mu_hat, iv)));
 }
 
 // one parameter: gradient sink (loss_grad mode) or best-parameter bookkeeping + Adam step on the packed state
-template <typename R>
+// PLAIN: Adam pass of a launch without freeze mask and parameter history (the stage-1 runs of Synthesize.static()):
+// the per-parameter tests on those pointers disappear from the gate loops.
+template <typename R, bool PLAIN>
 __device__ __forceinline__ void heis_apply(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int pi, R g, Pk4<R>& v) {
-  if (u.phase == PH_GRAD) {
+  if (!PLAIN && u.phase == PH_GRAD) {
     if (u.active) p.grad_out[u.off + (unsigned)pi] = g;
     return;
   }
   // v.th is still the pre-update parameter of the step being finished (optimization.py:70-73)
   if (u.store_best) v.best = v.th;
-  if (!(p.freeze && p.freeze[u.off + (unsigned)pi])) adam_inl(p, u, g, v.th, v.mu, v.nu);
+  if (PLAIN || !(p.freeze && p.freeze[u.off + (unsigned)pi])) adam_inl(p, u, g, v.th, v.mu, v.nu);
   if (u.active) {
     pk_store(pk + pi, v);
-    if (u.hist) p.hist_params[u.hist_off + pi] = v.th;
+    if (!PLAIN && u.hist) p.hist_params[u.hist_off + pi] = v.th;
   }
 }
 
@@ -510,32 +543,30 @@ __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const U
 
 // Fused one-qubit gate: finish the step (chain rule through the fusion, Adam), then the new (alpha, beta).
 // AX* >= 0: compile-time rotation axes (the selects fold away); AX0 == -2: axes from the gate metadata.
-template <typename R, int AX0, int AX1, int AX2>
+template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, const Su2Meta* md,
                                                 GateIn<R> in, R* cf, R* ax) {
   const int ax0 = AX0 == -2 ? md->axis[0] : AX0;
   const int ax1 = AX0 == -2 ? md->axis[1] : AX1;
   const int ax2 = AX0 == -2 ? md->axis[2] : AX2;
-  if (u.phase != PH_COEF) {
+  if (PLAIN || u.phase != PH_COEF) {
+    // chain rule through G = R_2 R_1 R_0: g_2 = S . e_2, g_1 = S . (R_2 e_1) = (R_2^T S) . e_1,
+    // g_0 = (R_1^T R_2^T S) . e_0: rotate S backwards (no products with the zero entries of unit vectors)
     const R C2 = in.c2 * in.c2 - in.s2 * in.s2, S2 = R(2) * in.c2 * in.s2;
     const R C3 = in.c3 * in.c3 - in.s3 * in.s3, S3 = R(2) * in.c3 * in.s3;
-    R x1 = ax1 == 0, y1 = ax1 == 1, z1 = ax1 == 2;
-    rot_axis(ax2, C3, S3, x1, y1, z1);
-    R x0 = ax0 == 0, y0 = ax0 == 1, z0 = ax0 == 2;
-    rot_axis(ax1, C2, S2, x0, y0, z0);
-    rot_axis(ax2, C3, S3, x0, y0, z0);
-    const R g2 = sel3(ax2, in.sx, in.sy, in.sz);
-    const R g1 = x1 * in.sx + y1 * in.sy + z1 * in.sz;
-    const R g0 = x0 * in.sx + y0 * in.sy + z0 * in.sz;
-    if (in.pi2 >= 0) heis_apply(p, u, pk, in.pi2, g2, in.v2);
-    if (in.pi1 >= 0) heis_apply(p, u, pk, in.pi1, g1, in.v1);
-    if (in.pi0 >= 0) heis_apply(p, u, pk, in.pi0, g0, in.v0);
+    R sx = in.sx, sy = in.sy, sz = in.sz;
+    const R g2 = sel3(ax2, sx, sy, sz);
+    rot_axis(ax2, C3, -S3, sx, sy, sz);
+    const R g1 = sel3(ax1, sx, sy, sz);
+    rot_axis(ax1, C2, -S2, sx, sy, sz);
+    const R g0 = sel3(ax0, sx, sy, sz);
+    if (in.pi2 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi2, g2, in.v2);
+    if (in.pi1 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi1, g1, in.v1);
+    if (in.pi0 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi0, g0, in.v0);
   }
   if (!u.skip_coef) {
     R c0 = R(1), s0 = R(0), c1 = R(1), s1 = R(0), c2 = R(1), s2 = R(0);
-    if (ax0 >= 0) sincos_inl(in.v0.th * R(0.5), s0, c0);
-    if (ax1 >= 0) sincos_inl(in.v1.th * R(0.5), s1, c1);
-    if (ax2 >= 0) sincos_inl(in.v2.th * R(0.5), s2, c2);
+    sincos3(ax0 >= 0, ax1 >= 0, ax2 >= 0, in.v0.th * R(0.5), in.v1.th * R(0.5), in.v2.th * R(0.5), s0, c0, s1, c1, s2, c2);
     R ar, ai, br, bi;
     su2_of(ax0, c0, s0, ar, ai, br, bi);
     su2_lmul_axis(ax1, c1, s1, ar, ai, br, bi);
@@ -544,7 +575,7 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
     // ZYZ form for the forward sweep: alpha = cy p_a, beta = sy p_b, u_out = p_b conj(p_a), u_in = conj(p_a p_b)
     const R na = ar * ar + ai * ai, nb = br * br + bi * bi;
     const bool oka = na > R(1e-30), okb = nb > R(1e-30);
-    const R ia = oka ? rsqrt_r(na) : R(0), ib = okb ? rsqrt_r(nb) : R(0);
+    const R ia = oka ? rsqrt_fast(na) : R(0), ib = okb ? rsqrt_fast(nb) : R(0);
     const R par = oka ? ar * ia : R(1), pai = ai * ia, pbr = okb ? br * ib : R(1), pbi = bi * ib;
     cf[0] = na * ia; cf[1] = nb * ib;
     cf[2] = pbr * par + pbi * pai; cf[3] = pbi * par - pbr * pai;
@@ -557,7 +588,7 @@ constexpr int AXP_XYZ = 0 | (1 << 4) | (2 << 8);
 constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
 
 // gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined
-template <typename R, int AX0, int AX1, int AX2>
+template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end,
                                               int stride, R* coef, R* aux) {
   constexpr int SW = HEIS_SU2_WORDS;
@@ -566,17 +597,21 @@ __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const UpdCtx<
   for (int g = g0; g < g_end; g += stride) {
     const int gn = g + stride;
     const GateIn<R> nxt = heis_gate_load(p, u, pk, gn < g_end, p.su2 + gn, coef + SW * gn, aux + 4 * gn);
-    heis_su2_update<R, AX0, AX1, AX2>(p, u, pk, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
+    heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
     cur = nxt;
   }
 }
 template <typename R>
-__device__ __forceinline__ void heis_su2_loop_any(int axp, const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int g0,
-                                                  int g_end, int stride, R* coef, R* aux) {
-  if (axp == AXP_XYZ) heis_su2_loop<R, 0, 1, 2>(p, u, pk, g0, g_end, stride, coef, aux);
-  else if (axp == AXP_ZXZ) heis_su2_loop<R, 2, 0, 2>(p, u, pk, g0, g_end, stride, coef, aux);
-  else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1>(p, u, pk, g0, g_end, stride, coef, aux);
-  else heis_su2_loop<R, -2, -2, -2>(p, u, pk, g0, g_end, stride, coef, aux);
+__device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk,
+                                                  int g0, int g_end, int stride, R* coef, R* aux) {
+  if (axp == AXP_XYZ) {
+    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, u, pk, g0, g_end, stride, coef, aux);
+    else heis_su2_loop<R, 0, 1, 2, false>(p, u, pk, g0, g_end, stride, coef, aux);
+  } else if (axp == AXP_ZXZ) {
+    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, u, pk, g0, g_end, stride, coef, aux);
+    else heis_su2_loop<R, 2, 0, 2, false>(p, u, pk, g0, g_end, stride, coef, aux);
+  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, u, pk, g0, g_end, stride, coef, aux);
+  else heis_su2_loop<R, -2, -2, -2, false>(p, u, pk, g0, g_end, stride, coef, aux);
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -647,6 +682,7 @@ heis_kernel(const KParams<R> p) {
   LayerBar lb;
   lb.id = skew ? (grp_b ? 2 : 1) : 0;
   lb.cnt = skew ? (grp_b ? (int)blockDim.x - p.skew_split : p.skew_split) : (int)blockDim.x;
+  lb.every = p.sync_every; lb.every_bwd = p.sync_every_bwd;
   if (grp_b) cta_sync();
 
   R best = R(0), best_reg_v = R(0);
@@ -673,30 +709,47 @@ heis_kernel(const KParams<R> p) {
         u.ibc1 = R(1) / u.bc1; u.ibc2 = R(1) / u.bc2;
       }
       // surface gates (slots < NQ) and block gates (the rest) each share one axis pattern in the templates
-      heis_su2_loop_any(p.axp_surface, p, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
-      heis_su2_loop_any(p.axp_block, p, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
-      for (int k = m; k < p.n_cp; k += TPS) {
-        const CpMeta* md = p.cp + k;
-        R* cf = coef_cp + CW * k;
-        const int pi = md->pidx;
-        const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
-                            (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
-        Pk4<R> v;
-        if (pi >= 0) v = pk_load(pk + pi); else v.th = R(md->cangle);
-        // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
-        if (phase != PH_COEF && pi >= 0) heis_apply(p, u, pk, pi, add_rn(cf[0], cf[2]), v);
-        const R th = v.th;
-        if (!u.skip_coef) {
-          R s = R(1), c = R(0);                  // half angle; CZ = CP(pi): cos(pi/2) = 0 exactly
-          if (!md->is_cz) sincos_inl(th * R(0.5), s, c);
-          R rs = R(0);
-          if (pen_on) {
-            R val, slope;
-            penalty_eval(p.pen, th, val, slope);
-            reg_part += val;
-            rs = mul_rn(p.pen.r, slope);
+      // plain: an Adam pass (not the first, coefficient-only one) without freeze mask and parameter history
+      const bool plain = phase == PH_ADAM && p.freeze == nullptr && p.hist_params == nullptr;
+      heis_su2_loop_any(p.axp_surface, plain, p, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any(p.axp_block, plain, p, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
+      // entangler angles, software pipelined like the fused-gate loops: the packed state of the next gate is
+      // requested before the current one is processed
+      {
+        int k = m;
+        int pi_n = -1;
+        Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
+        if (k < p.n_cp) { pi_n = p.cp[k].pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
+#pragma unroll 1
+        for (; k < p.n_cp; k += TPS) {
+          const CpMeta* md = p.cp + k;
+          R* cf = coef_cp + CW * k;
+          const int pi = pi_n;
+          Pk4<R> v = v_n;
+          const int kn = k + TPS;
+          if (kn < p.n_cp) { pi_n = p.cp[kn].pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
+          const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
+                              (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
+          if (pi < 0) v.th = R(md->cangle);
+          // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
+          if (phase != PH_COEF && pi >= 0) {
+            const R g = add_rn(cf[0], cf[2]);
+            if (plain) heis_apply<R, true>(p, u, pk, pi, g, v);
+            else heis_apply<R, false>(p, u, pk, pi, g, v);
           }
-          cf[0] = c; cf[1] = s; cf[2] = rs;
+          const R th = v.th;
+          if (!u.skip_coef) {
+            R s = R(1), c = R(0);                  // half angle; CZ = CP(pi): cos(pi/2) = 0 exactly
+            if (!md->is_cz) sincos_inl(th * R(0.5), s, c);
+            R rs = R(0);
+            if (pen_on) {
+              R val, slope;
+              penalty_eval_fast(p.pen, th, val, slope);
+              reg_part += val;
+              rs = mul_rn(p.pen.r, slope);
+            }
+            cf[0] = c; cf[1] = s; cf[2] = rs;
+          }
         }
       }
     }
@@ -852,6 +905,11 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   p.coef_stride = heis_coef_stride(p.n_su2, p.n_cp, SWP::NSTAGE);
   const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes, (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT);
   p.spb = g.spb;
+  // CTA barriers inside the sweeps (they keep the warps on the same instruction-cache lines): one at the start
+  // of each sweep is enough to stop the warps drifting apart; a barrier per layer costs 7 % (B200, C3)
+  p.sync_every = p.sync_every_bwd = HEIS_SYNC_EVERY_DEFAULT;
+  if (const char* e = getenv("CPF_HEIS_SYNC_EVERY")) { int v = atoi(e); if (v >= 0) p.sync_every = p.sync_every_bwd = v; }
+  if (const char* e = getenv("CPF_HEIS_SYNC_BWD")) { int v = atoi(e); if (v >= 0) p.sync_every_bwd = v; }
   // phase skew: env CPF_HEIS_SKEW = percentage of the CTA's warps in group A (0 = off)
   p.skew_split = 0;
   {

@@ -1,8 +1,10 @@
 #!/bin/bash
-# ncu full capture of heis_kernel on a short C3 run (extra env passed through), plus repeated event timings
+# ncu full capture of heis_kernel on a short C3 run with full residency (57 samples per SM), then GPU tests + bench
 mkdir -p gpurun_out
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:^heis_kernel -c 1 -f -o gpurun_out/prof_heis \
-  python tools/prof_c3.py 12500 40 > gpurun_out/ncu_full.log 2>&1
+  python tools/prof_c3.py 8436 40 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
-for i in 1 2; do timeout 300 python tools/prof_engine.py --T 400 --reps 4 2>&1 | tail -4; done
-CPF_HEIS_SKEW=36 timeout 300 python tools/prof_engine.py --T 400 --reps 4 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-cpu-baseline --no-static > gpurun_out/bench_quick.json; python -c "
+import json
+d=json.load(open('gpurun_out/bench_quick.json')); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['clocks'])"
