@@ -28,7 +28,7 @@
 
 namespace cpf {
 
-// Shared-memory slot of a fused one-qubit gate, 8 words: cy, sy | u_out | u_in (surface) / A (lower-qubit gate) /
+// Shared-memory slot of a fused one-qubit gate, 8 words: ty, sy (lifting form of Ry: ty = -sy / (1 + cy)) | u_out | u_in (surface) / A (lower-qubit gate) /
 // A B e^{ia} (higher-qubit gate) | B (lower-qubit gate).  The backward sweep overwrites words 0..2 with the
 // gradient sums (S_X, S_Y, S_Z).  The SO(3) rows of the backward sweep are NOT kept per gate: they are
 // produced one layer at a time in a staging area (HEIS_STAGE_WORDS per gate of a layer), which keeps the
@@ -104,11 +104,11 @@ struct HeisSweep {
   // loss and the Hermitian part that seeds the backward sweep do not see it).  u_in merges with the block's
   // CP phase and with the u_out still pending on the same qubits into one diagonal (1, B, A, A B e^{ia}),
   // prepared by the parameter phase: a block costs 3 + 4 + 4 = 11 FMA per amplitude instead of 1 + 8 + 8.
-  // Slot words during the forward sweep: 0 cy; 1 sy; [2,4) u_out; lower-qubit slot [4,8) A, B;
+  // Slot words during the forward sweep: 0 ty = -sy / (1 + cy); 1 sy; [2,4) u_out; lower-qubit slot [4,8) A, B;
   // higher-qubit slot [4,6) A B e^{ia}; surface slots [4,6) u_in.
   template <int BP>
   static __device__ __forceinline__ void ry_fwd(V (&yr)[N], V (&yi)[N], const R* cf) {
-    CO::template ry_reg<BP>(yr, yi, cf[0], cf[1]);
+    CO::template ry_lift<BP>(yr, yi, cf[0], cf[1]);
   }
   template <int Q>
   static __device__ __forceinline__ void surface_fwd(V (&yr)[N], V (&yi)[N], const R* coef) {
@@ -320,7 +320,8 @@ struct HeisSweep {
   }
   // SO(3) rows of G' = diag(1, u_out) Ry diag(1, u_in') = Rz3(phi_out) Ry3(theta) Rz3(phi_in'), stored transposed
   // (M = R^T) in rows of 4 words.  (ci, si) = u_in' = u_in e^{i a/2} carries the block's share of its CP gate.
-  static __device__ __forceinline__ void zyz_to_so3(R* st, R cy, R sy, R co, R so, R ci, R si) {
+  static __device__ __forceinline__ void zyz_to_so3(R* st, R ty, R sy, R co, R so, R ci, R si) {
+    const R cy = R(1) + ty * sy;   // 1 - tan(phi/2) sin phi = cos phi
     const R ct = cy * cy - sy * sy, sth = R(2) * cy * sy;
     const R cc = ct * ci, cs2 = ct * si;
     Vec4Load<R>::st(st, co * cc - so * si, so * cc + co * si, -sth * ci, R(0));
@@ -413,6 +414,8 @@ __device__ __forceinline__ void pk_store(Pk4<double>* q, const Pk4<double>& v) {
 
 __device__ __forceinline__ float rsqrt_fast(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 __device__ __forceinline__ double rsqrt_fast(double a) { return rsqrt_r(a); }
+__device__ __forceinline__ float rcp_fast(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
 static __device__ __noinline__ SinCos<float> sincos_slow_v(float x) { float s, c; sincosf(x, &s, &c); return {s, c}; }
 // sin/cos for the parameter phase, inlined so the three evaluations of a fused gate interleave
 __device__ __forceinline__ void sincos_core(float x, float& s, float& c) {
@@ -577,7 +580,9 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
     const bool oka = na > R(1e-30), okb = nb > R(1e-30);
     const R ia = oka ? rsqrt_fast(na) : R(0), ib = okb ? rsqrt_fast(nb) : R(0);
     const R par = oka ? ar * ia : R(1), pai = ai * ia, pbr = okb ? br * ib : R(1), pbi = bi * ib;
-    cf[0] = na * ia; cf[1] = nb * ib;
+    // Ry by phi with cos phi = cy = |alpha| >= 0, sin phi = sy = |beta| >= 0, in lifting form (Cols::ry_lift)
+    const R cyv = na * ia, syv = nb * ib;
+    cf[0] = -syv * rcp_fast(R(1) + cyv); cf[1] = syv;
     cf[2] = pbr * par + pbi * pai; cf[3] = pbi * par - pbr * pai;
     cf[4] = par * pbr - pai * pbi; cf[5] = -(par * pbi + pai * pbr);
   }
@@ -592,13 +597,17 @@ template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end,
                                               int stride, R* coef, R* aux) {
   constexpr int SW = HEIS_SU2_WORDS;
+  // two gates ahead: the L2 round trip of the packed state is longer than the update of one gate
   GateIn<R> cur = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, coef + SW * g0, aux + 4 * g0);
+  GateIn<R> nxt = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, coef + SW * (g0 + stride),
+                                 aux + 4 * (g0 + stride));
 #pragma unroll 1
   for (int g = g0; g < g_end; g += stride) {
-    const int gn = g + stride;
-    const GateIn<R> nxt = heis_gate_load(p, u, pk, gn < g_end, p.su2 + gn, coef + SW * gn, aux + 4 * gn);
+    const int gn = g + 2 * stride;
+    const GateIn<R> nn = heis_gate_load(p, u, pk, gn < g_end, p.su2 + gn, coef + SW * gn, aux + 4 * gn);
     heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
     cur = nxt;
+    nxt = nn;
   }
 }
 template <typename R>
