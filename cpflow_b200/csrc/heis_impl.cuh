@@ -50,6 +50,13 @@ template <typename R> inline int heis_target_words(int n, int cpt) {
   return (N / cpt) * (N + 1) * 2 * cpt;
 }
 
+// Gate metadata as the kernel reads it, staged in shared memory by the prologue (the global-memory records of
+// program.hpp sat on the critical path of every gate update: a dependent L2 round trip before the load of the
+// packed state).  Constant angles (pidx < 0) stay in the global records.
+struct __align__(8) HSu2 { int16_t pidx[3]; uint16_t axes; };                   // axes: 4 bits per rotation, 15 = unused
+struct __align__(8) HCp { int16_t pidx; uint16_t flags; int16_t prev_lo, prev_hi; };   // flags: 1 penalised, 2 CZ
+__host__ __device__ inline int heis_meta_bytes(int n_su2, int n_cp) { return (8 * (n_su2 + n_cp) + 15) & ~15; }
+
 template <typename R, int NQ, int CPT>
 struct HCfg {
   static constexpr int N = 1 << NQ;
@@ -330,16 +337,16 @@ struct HeisSweep {
   }
   // Staging of one layer (blocks k0 .. k0 + NBL - 1): the sample's lanes split the layer's 2 NBL fused gates.
   // u_in of a block gate is recovered from the merged diagonal: u_in = A conj(pending u_out of the previous gate).
-  static __device__ __forceinline__ void stage_layer(const KParams<R>& p, int k0, int K, const R* coef, const R* cph0,
+  static __device__ __forceinline__ void stage_layer(const HCp* mcp, int k0, int K, const R* coef, const R* cph0,
                                                      R* stage, int m) {
     const int nb = K - k0 < NBL ? K - k0 : NBL;
 #pragma unroll 1
     for (int j = m; j < 2 * nb; j += TPS) {
       const int k = k0 + (j >> 1), hi = j & 1;
-      const CpMeta* md = p.cp + k;
+      const HCp md = mcp[k];
       const R* cl = coef + SW * (NQ + 2 * k);
       const R* cf = cl + SW * hi;
-      const R* pv = coef + SW * (hi ? md->prev_hi : md->prev_lo);
+      const R* pv = coef + SW * (hi ? md.prev_hi : md.prev_lo);
       const R* cc = cph0 + CW * k;
       const R dr = cl[4 + 2 * hi], di = cl[5 + 2 * hi];          // A (lower-qubit gate) / B (higher-qubit gate)
       const R pr = pv[2], pi = pv[3];
@@ -355,8 +362,8 @@ struct HeisSweep {
       zyz_to_so3(stage + STW * q, cf[0], cf[1], cf[2], cf[3], cf[4], cf[5]);
     }
   }
-  static __device__ __forceinline__ void backward(const KParams<R>& p, const LayerBar lb, R* coef, R* stage, int m,
-                                                  V (&h)[N]) {
+  static __device__ __forceinline__ void backward(const KParams<R>& p, const HCp* mcp, const LayerBar lb, R* coef,
+                                                  R* stage, int m, V (&h)[N]) {
     const int K = p.n_cp;
     R* cph0 = coef + SW * p.n_su2;
 #pragma unroll 1
@@ -364,7 +371,7 @@ struct HeisSweep {
     for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL) {
       if (li == 0 && lb.every_bwd > 0) lb.sync();
       li = li + 1 == lb.every_bwd ? 0 : li + 1;
-      stage_layer(p, k0, K, coef, cph0, stage, m);
+      stage_layer(mcp, k0, K, coef, cph0, stage, m);
       __syncwarp();
       blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
       __syncwarp();
@@ -521,19 +528,21 @@ __device__ __forceinline__ void su2_lmul_axis(int a, R c, R s, R& ar, R& ai, R& 
 // L2 round trips (theta, Adam moments, half-angle cos/sin of the fused rotations) overlap the arithmetic.
 template <typename R>
 struct GateIn {
-  int pi0, pi1, pi2;
+  int pi0, pi1, pi2, axes;
   Pk4<R> v0, v1, v2;
   R sx, sy, sz, c2, s2, c3, s3;
 };
 template <typename R>
 __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const UpdCtx<R>& u, const Pk4<R>* pk, bool valid,
-                                                    const Su2Meta* md, const R* cf, const R* ax) {
+                                                    const Su2Meta* md, const HSu2* ms, const R* cf, const R* ax) {
   GateIn<R> in;
-  in.pi0 = in.pi1 = in.pi2 = -1;
+  in.pi0 = in.pi1 = in.pi2 = -1; in.axes = 0xfff;
   in.v0 = in.v1 = in.v2 = Pk4<R>{R(0), R(0), R(0), R(0)};
   in.sx = in.sy = in.sz = in.c2 = in.s2 = in.c3 = in.s3 = R(0);
   if (!valid) return in;
-  in.pi0 = md->pidx[0]; in.pi1 = md->pidx[1]; in.pi2 = md->pidx[2];
+  const HSu2 hm = *ms;
+  in.pi0 = hm.pidx[0]; in.pi1 = hm.pidx[1]; in.pi2 = hm.pidx[2];
+  in.axes = hm.axes;
   if (in.pi0 >= 0) in.v0 = pk_load(pk + in.pi0); else in.v0.th = R(md->cangle[0]);
   if (in.pi1 >= 0) in.v1 = pk_load(pk + in.pi1); else in.v1.th = R(md->cangle[1]);
   if (in.pi2 >= 0) in.v2 = pk_load(pk + in.pi2); else in.v2.th = R(md->cangle[2]);
@@ -549,9 +558,10 @@ __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const U
 template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, const Su2Meta* md,
                                                 GateIn<R> in, R* cf, R* ax) {
-  const int ax0 = AX0 == -2 ? md->axis[0] : AX0;
-  const int ax1 = AX0 == -2 ? md->axis[1] : AX1;
-  const int ax2 = AX0 == -2 ? md->axis[2] : AX2;
+  const int a0 = in.axes & 15, a1 = (in.axes >> 4) & 15, a2 = (in.axes >> 8) & 15;   // 15 = unused slot
+  const int ax0 = AX0 == -2 ? (a0 == 15 ? -1 : a0) : AX0;
+  const int ax1 = AX0 == -2 ? (a1 == 15 ? -1 : a1) : AX1;
+  const int ax2 = AX0 == -2 ? (a2 == 15 ? -1 : a2) : AX2;
   if (PLAIN || u.phase != PH_COEF) {
     // chain rule through G = R_2 R_1 R_0: g_2 = S . e_2, g_1 = S . (R_2 e_1) = (R_2^T S) . e_1,
     // g_0 = (R_1^T R_2^T S) . e_0: rotate S backwards (no products with the zero entries of unit vectors)
@@ -594,33 +604,34 @@ constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
 
 // gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined
 template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
-__device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end,
-                                              int stride, R* coef, R* aux) {
+__device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, Pk4<R>* pk, int g0,
+                                              int g_end, int stride, R* coef, R* aux) {
   constexpr int SW = HEIS_SU2_WORDS;
   // two gates ahead: the L2 round trip of the packed state is longer than the update of one gate
-  GateIn<R> cur = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, coef + SW * g0, aux + 4 * g0);
-  GateIn<R> nxt = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, coef + SW * (g0 + stride),
-                                 aux + 4 * (g0 + stride));
+  GateIn<R> cur = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
+  GateIn<R> nxt = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride,
+                                 coef + SW * (g0 + stride), aux + 4 * (g0 + stride));
 #pragma unroll 1
   for (int g = g0; g < g_end; g += stride) {
     const int gn = g + 2 * stride;
-    const GateIn<R> nn = heis_gate_load(p, u, pk, gn < g_end, p.su2 + gn, coef + SW * gn, aux + 4 * gn);
+    const GateIn<R> nn = heis_gate_load(p, u, pk, gn < g_end, p.su2 + gn, ms + gn, coef + SW * gn, aux + 4 * gn);
     heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
     cur = nxt;
     nxt = nn;
   }
 }
 template <typename R>
-__device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk,
-                                                  int g0, int g_end, int stride, R* coef, R* aux) {
+__device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const HSu2* ms,
+                                                  const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end, int stride, R* coef,
+                                                  R* aux) {
   if (axp == AXP_XYZ) {
-    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, u, pk, g0, g_end, stride, coef, aux);
-    else heis_su2_loop<R, 0, 1, 2, false>(p, u, pk, g0, g_end, stride, coef, aux);
+    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    else heis_su2_loop<R, 0, 1, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
   } else if (axp == AXP_ZXZ) {
-    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, u, pk, g0, g_end, stride, coef, aux);
-    else heis_su2_loop<R, 2, 0, 2, false>(p, u, pk, g0, g_end, stride, coef, aux);
-  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, u, pk, g0, g_end, stride, coef, aux);
-  else heis_su2_loop<R, -2, -2, -2, false>(p, u, pk, g0, g_end, stride, coef, aux);
+    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    else heis_su2_loop<R, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+  else heis_su2_loop<R, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -637,7 +648,9 @@ heis_kernel(const KParams<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   R* s_target = reinterpret_cast<R*>(smem_raw);
-  R* s_coef = reinterpret_cast<R*>(smem_raw + p.target_bytes);
+  HSu2* s_su2 = reinterpret_cast<HSu2*>(smem_raw + p.target_bytes);
+  HCp* s_cp = reinterpret_cast<HCp*>(s_su2 + p.n_su2);
+  R* s_coef = reinterpret_cast<R*>(smem_raw + p.target_bytes + heis_meta_bytes(p.n_su2, p.n_cp));
 
   const int tid = threadIdx.x;
   // ---- prologue: TMA-stage V^dag (packed by pack_target_heis_kernel) ----
@@ -649,6 +662,26 @@ heis_kernel(const KParams<R> p) {
   if (tid == 0) {
     mbar_expect_tx(&s_bar, (uint32_t)p.target_bytes);
     tma_bulk_g2s(s_target, p.target_packed, (uint32_t)p.target_bytes, &s_bar);
+  }
+  // gate metadata -> shared memory (compact records)
+  for (int g = tid; g < p.n_su2; g += blockDim.x) {
+    const Su2Meta* md = p.su2 + g;
+    HSu2 hm;
+    unsigned axes = 0;
+    for (int j = 0; j < 3; ++j) {
+      hm.pidx[j] = (int16_t)md->pidx[j];
+      axes |= (unsigned)(md->axis[j] < 0 ? 15 : md->axis[j]) << (4 * j);
+    }
+    hm.axes = (uint16_t)axes;
+    s_su2[g] = hm;
+  }
+  for (int k = tid; k < p.n_cp; k += blockDim.x) {
+    const CpMeta* md = p.cp + k;
+    HCp hm;
+    hm.pidx = (int16_t)md->pidx;
+    hm.flags = (uint16_t)(((p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0) ? 1 : 0) | (md->is_cz ? 2 : 0));
+    hm.prev_lo = md->prev_lo; hm.prev_hi = md->prev_hi;
+    s_cp[k] = hm;
   }
   __syncthreads();
   mbar_wait(&s_bar, 0);
@@ -720,26 +753,26 @@ heis_kernel(const KParams<R> p) {
       // surface gates (slots < NQ) and block gates (the rest) each share one axis pattern in the templates
       // plain: an Adam pass (not the first, coefficient-only one) without freeze mask and parameter history
       const bool plain = phase == PH_ADAM && p.freeze == nullptr && p.hist_params == nullptr;
-      heis_su2_loop_any(p.axp_surface, plain, p, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
-      heis_su2_loop_any(p.axp_block, plain, p, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any(p.axp_surface, plain, p, s_su2, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
       // entangler angles, software pipelined like the fused-gate loops: the packed state of the next gate is
       // requested before the current one is processed
       {
         int k = m;
         int pi_n = -1;
         Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
-        if (k < p.n_cp) { pi_n = p.cp[k].pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
+        HCp md_n = HCp{-1, 0, 0, 0};
+        if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
 #pragma unroll 1
         for (; k < p.n_cp; k += TPS) {
-          const CpMeta* md = p.cp + k;
+          const HCp md = md_n;
           R* cf = coef_cp + CW * k;
           const int pi = pi_n;
           Pk4<R> v = v_n;
           const int kn = k + TPS;
-          if (kn < p.n_cp) { pi_n = p.cp[kn].pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
-          const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 &&
-                              (p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0);
-          if (pi < 0) v.th = R(md->cangle);
+          if (kn < p.n_cp) { md_n = s_cp[kn]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
+          const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 && (md.flags & 1) != 0;
+          if (pi < 0) v.th = R(p.cp[k].cangle);
           // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
           if (phase != PH_COEF && pi >= 0) {
             const R g = add_rn(cf[0], cf[2]);
@@ -749,7 +782,7 @@ heis_kernel(const KParams<R> p) {
           const R th = v.th;
           if (!u.skip_coef) {
             R s = R(1), c = R(0);                  // half angle; CZ = CP(pi): cos(pi/2) = 0 exactly
-            if (!md->is_cz) sincos_inl(th * R(0.5), s, c);
+            if (!(md.flags & 2)) sincos_inl(th * R(0.5), s, c);
             R rs = R(0);
             if (pen_on) {
               R val, slope;
@@ -766,11 +799,11 @@ heis_kernel(const KParams<R> p) {
     if (it == p.nsteps) break;
     // merged diagonals of the forward sweep: A = pending(lo) u_in(lo), B = pending(hi) u_in(hi), A B e^{ia}
     for (int k = m; k < p.n_cp; k += TPS) {
-      const CpMeta* md = p.cp + k;
+      const HCp md = s_cp[k];
       R* cl = coef + SW * (NQ + 2 * k);
       R* ch = cl + SW;
-      const R* pl = coef + SW * md->prev_lo;
-      const R* ph = coef + SW * md->prev_hi;
+      const R* pl = coef + SW * md.prev_lo;
+      const R* ph = coef + SW * md.prev_hi;
       const R* cc = coef_cp + CW * k;
       const R plr = pl[2], pli = pl[3], phr = ph[2], phi = ph[3];
       const R ar = plr * cl[4] - pli * cl[5], ai = plr * cl[5] + pli * cl[4];
@@ -843,7 +876,7 @@ heis_kernel(const KParams<R> p) {
     __syncwarp();
 
     // ---------------- Heisenberg sweep ----------------
-    SWP::backward(p, lb, coef, coef_cp + CW * p.n_cp, m, h);
+    SWP::backward(p, s_cp, lb, coef, coef_cp + CW * p.n_cp, m, h);
     __syncwarp();
     if (skew) cta_sync();
   }
@@ -912,7 +945,9 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   using C = HCfg<R, NQ, CPT>;
   p.n_sched = 0; p.n_red = 0;
   p.coef_stride = heis_coef_stride(p.n_su2, p.n_cp, SWP::NSTAGE);
-  const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes, (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT);
+  if (p.P > 32767) { err = "heis kernel: more than 32767 parameters"; return CPF_ERR_UNSUPPORTED; }
+  const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes + heis_meta_bytes(p.n_su2, p.n_cp),
+                                       (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT);
   p.spb = g.spb;
   // CTA barriers inside the sweeps (they keep the warps on the same instruction-cache lines): one at the start
   // of each sweep is enough to stop the warps drifting apart; a barrier per layer costs 7 % (B200, C3)
