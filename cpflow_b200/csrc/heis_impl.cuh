@@ -34,10 +34,14 @@ namespace cpf {
 // produced one layer at a time in a staging area (HEIS_STAGE_WORDS per gate of a layer), which keeps the
 // per-sample footprint small enough for two co-resident CTAs of 7-8 warps per SM.
 constexpr int HEIS_SU2_WORDS = 8;
-constexpr int HEIS_STAGE_WORDS = 12; // rows of M = R(G)^T padded to 4 words
+// Staged coefficients of a gate of the backward sweep, 16 words: two rows (ka, kb, k00, k01 | k02, k10, k11, k12)
+// of the lane-uniform update  send = ka e0 + kb e1;  e0' = k00 e0 + k01 e1 + k02 recv;  e1' = k10 e0 + k11 e1 + k12 recv:
+// row 0 for lanes that hold (I, Z) of the gate's qubit (0, 1, 1, 0 | 0, 0, m22, 1), row 1 for lanes that hold (X, Y)
+// (m20, m21, m00, m01 | m02, m10, m11, m12), M = R(G)^T.  A lane picks its row by address: no selects.
+constexpr int HEIS_STAGE_WORDS = 16;
 constexpr int HEIS_SYNC_EVERY_DEFAULT = 1 << 20;   // layers between CTA barriers inside a sweep (first layer always)
 constexpr int HEIS_SKEW_DEFAULT = 0;    // % of a CTA's warps in phase group A (heis_kernel); 0 = unskewed
-constexpr int HEIS_CP_WORDS = 4;     // cos(a/2), sin(a/2), r * penalty slope, - ; word 0 <- dL/da after the backward sweep
+constexpr int HEIS_CP_WORDS = 4;     // cos(a/2) >= 0, sin(a/2), r * penalty slope, -tan(a/4); word 0 <- dL/da after the backward sweep
 
 inline int heis_coef_stride(int n_su2, int n_cp, int n_stage) {
   int w = (HEIS_SU2_WORDS * n_su2 + HEIS_CP_WORDS * n_cp + HEIS_STAGE_WORDS * n_stage + 3) & ~3;
@@ -81,6 +85,17 @@ struct LayerBar {
 
 // CTA-wide barrier reached from different code positions by the two phase groups (plain bar.sync 0)
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// Store to shared memory under a predicate, without a branch (the compiler turns `if (lane == k) s[i] = v`
+// into BSSY / BRA / BSYNC sequences inside the sweeps).
+__device__ __forceinline__ void sts_if(bool on, float* q, float v) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.shared.f32 [%1], %2; }" ::"r"((int)on),
+               "r"((unsigned)__cvta_generic_to_shared(q)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_if(bool on, double* q, double v) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.shared.f64 [%1], %2; }" ::"r"((int)on),
+               "r"((unsigned)__cvta_generic_to_shared(q)), "d"(v) : "memory");
+}
 
 template <typename V> struct AddV;
 template <> struct AddV<float> { static __device__ __forceinline__ float add(float a, float b) { return a + b; }
@@ -211,17 +226,13 @@ struct HeisSweep {
   static __device__ __forceinline__ void su2_bwd(V (&hv)[N], const R* cf, R* sl, int m) {
     constexpr int BM = 1 << B;
     if constexpr (B < PB) {
-      if (m == 0) { sl[0] = T::get(hv[0], 1); sl[1] = T::get(hv[BM], 1); sl[2] = T::get(hv[BM], 0); }
-    } else {
-      if (m == (1 << (B - PB))) { sl[0] = T::get(hv[0], 0); sl[1] = T::get(hv[BM], 0); }
-      if (m == 0) sl[2] = T::get(hv[BM], 0);
-    }
-    R m00, m01, m02, m10, m11, m12, m20, m21, m22, pad;
-    Vec4Load<R>::ld(cf, m00, m01, m02, pad);
-    Vec4Load<R>::ld(cf + 4, m10, m11, m12, pad);
-    Vec4Load<R>::ld(cf + 8, m20, m21, m22, pad);
-    if constexpr (B < PB) {
+      const bool own = m == 0;
+      sts_if(own, sl, T::get(hv[0], 1)); sts_if(own, sl + 1, T::get(hv[BM], 1)); sts_if(own, sl + 2, T::get(hv[BM], 0));
       // x bit = xr: I = h[0][z], Z = h[0][z|1], X = h[1][z], Y = h[1][z|1]
+      R m20, m21, m00, m01, m02, m10, m11, m12;
+      Vec4Load<R>::ld(cf + 8, m20, m21, m00, m01);
+      Vec4Load<R>::ld(cf + 12, m02, m10, m11, m12);
+      const R m22 = cf[6];
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & BM) continue;
@@ -233,9 +244,15 @@ struct HeisSweep {
       // x bit is lane bit J: lanes with the bit clear hold (I, Z), lanes with it set hold (X, Y)
       constexpr int J = B - PB;
       const bool mb = ((m >> J) & 1) != 0;
-      const V ka = T::bc(mb ? m20 : R(0)), kb = T::bc(mb ? m21 : R(1));
-      const V k00 = T::bc(mb ? m00 : R(1)), k01 = T::bc(mb ? m01 : R(0)), k02 = T::bc(mb ? m02 : R(0));
-      const V k10 = T::bc(mb ? m10 : R(0)), k11 = T::bc(mb ? m11 : m22), k12 = T::bc(mb ? m12 : R(1));
+      const bool own = m == (1 << J);
+      sts_if(own, sl, T::get(hv[0], 0)); sts_if(own, sl + 1, T::get(hv[BM], 0));
+      sts_if(m == 0, sl + 2, T::get(hv[BM], 0));
+      const R* row = cf + (mb ? 8 : 0);
+      R a, b, c00, c01, c02, c10, c11, c12;
+      Vec4Load<R>::ld(row, a, b, c00, c01);
+      Vec4Load<R>::ld(row + 4, c02, c10, c11, c12);
+      const V ka = T::bc(a), kb = T::bc(b), k00 = T::bc(c00), k01 = T::bc(c01), k02 = T::bc(c02), k10 = T::bc(c10),
+              k11 = T::bc(c11), k12 = T::bc(c12);
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & BM) continue;
@@ -257,30 +274,31 @@ struct HeisSweep {
   // for coefficients whose x bits on the two qubits differ, the pairs (e00, e11) and (e01, e10) of every
   // (z1, z2) quad by a/2.  cf: cos(a/2), sin(a/2); word 0 receives dL/da = -(h_II - h_ZI - h_IZ + h_ZZ)/2
   // (Z-type coefficients: they do not see the Rz shuffle).
+  // Both pair rotations in lifting form (three shears each: 6 instead of 8 FMA-pipe instructions per quad): the
+  // parameter phase keeps cos(a/2) >= 0 (CP(a) = CP(a - 2 pi)), so t = -tan(a/4) = -s / (1 + c) lies in [-1, 1].
   template <typename E>
-  static __device__ __forceinline__ void zz_quad(E& e00, E& e01, E& e10, E& e11, E cl, E sl, E s2) {
+  static __device__ __forceinline__ void zz_quad(E& e00, E& e01, E& e10, E& e11, E tl, E sl, E t2, E s2) {
     using O = VT<R, sizeof(E) == sizeof(R) ? 1 : 2>;
-    const E a = e00, b = e01, c = e10, d = e11;
-    e00 = O::sub(O::mul(cl, a), O::mul(sl, d));
-    e11 = O::fma(sl, a, O::mul(cl, d));
-    e01 = O::sub(O::mul(cl, b), O::mul(s2, c));
-    e10 = O::fma(s2, b, O::mul(cl, c));
+    E a = O::fma(tl, e11, e00), b = O::fma(t2, e10, e01);
+    e11 = O::fma(sl, a, e11); e10 = O::fma(s2, b, e10);
+    e00 = O::fma(tl, e11, a); e01 = O::fma(t2, e10, b);
   }
   template <int B1, int B2>
   static __device__ __forceinline__ void phase_bwd(V (&hv)[N], R* cf, int m) {
     constexpr int M1 = 1 << B1, M2 = 1 << B2;
-    const R c = cf[0], s = cf[1];
+    const R s = cf[1], t = cf[3];
     const R g11 = R(-0.5) * ((T::get(hv[0], 0) - T::get(hv[M1], 0)) - (T::get(hv[M2], 0) - T::get(hv[M1 | M2], 0)));
     __syncwarp();
-    if (m == 0) cf[0] = g11;
+    sts_if(m == 0, cf, g11);
     if constexpr (B1 >= PB && B2 >= PB) {
       // both x bits are lane bits: one case per lane, packed arithmetic over xr
       const bool x1 = xlane<B1>(m), x2 = xlane<B2>(m), on = x1 != x2;
-      const V cl = T::bc(on ? c : R(1)), sl = T::bc(on ? s : R(0)), s2 = T::bc(on ? (x1 ? s : -s) : R(0));
+      const V tl = T::bc(on ? t : R(0)), sl = T::bc(on ? s : R(0));
+      const V t2 = T::bc(on ? (x1 ? t : -t) : R(0)), s2 = T::bc(on ? (x1 ? s : -s) : R(0));
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & (M1 | M2)) continue;
-        zz_quad<V>(hv[z], hv[z | M2], hv[z | M1], hv[z | M1 | M2], cl, sl, s2);
+        zz_quad<V>(hv[z], hv[z | M2], hv[z | M1], hv[z | M1 | M2], tl, sl, t2, s2);
       }
     } else {
       // one of the bits is amplitude bit 0, whose x bit is the packed component xr: scalar per component
@@ -289,13 +307,13 @@ struct HeisSweep {
 #pragma unroll
       for (int xr = 0; xr < XR; ++xr) {
         const bool x1 = B1 >= PB ? xl : xr != 0, x2 = B2 >= PB ? xl : xr != 0, on = x1 != x2;
-        const R cl = on ? c : R(1), sl = on ? s : R(0), s2 = on ? (x1 ? s : -s) : R(0);
+        const R tl = on ? t : R(0), sl = on ? s : R(0), t2 = on ? (x1 ? t : -t) : R(0), s2 = on ? (x1 ? s : -s) : R(0);
 #pragma unroll
         for (int z = 0; z < N; ++z) {
           if (z & (M1 | M2)) continue;
           R e00 = T::get(hv[z], xr), e01 = T::get(hv[z | M2], xr), e10 = T::get(hv[z | M1], xr),
             e11 = T::get(hv[z | M1 | M2], xr);
-          zz_quad<R>(e00, e01, e10, e11, cl, sl, s2);
+          zz_quad<R>(e00, e01, e10, e11, tl, sl, t2, s2);
           setc(hv[z], xr, e00); setc(hv[z | M2], xr, e01); setc(hv[z | M1], xr, e10); setc(hv[z | M1 | M2], xr, e11);
         }
       }
@@ -331,9 +349,12 @@ struct HeisSweep {
     const R cy = R(1) + ty * sy;   // 1 - tan(phi/2) sin phi = cos phi
     const R ct = cy * cy - sy * sy, sth = R(2) * cy * sy;
     const R cc = ct * ci, cs2 = ct * si;
-    Vec4Load<R>::st(st, co * cc - so * si, so * cc + co * si, -sth * ci, R(0));
-    Vec4Load<R>::st(st + 4, -(co * cs2 + so * ci), co * ci - so * cs2, sth * si, R(0));
-    Vec4Load<R>::st(st + 8, co * sth, so * sth, ct, R(0));
+    // rows of M = R^T: (m00 m01 m02) = (co cc - so si, so cc + co si, -sth ci), (m10 m11 m12) =
+    // (-(co cs2 + so ci), co ci - so cs2, sth si), (m20 m21 m22) = (co sth, so sth, ct)
+    Vec4Load<R>::st(st, R(0), R(1), R(1), R(0));
+    Vec4Load<R>::st(st + 4, R(0), R(0), ct, R(1));
+    Vec4Load<R>::st(st + 8, co * sth, so * sth, co * cc - so * si, so * cc + co * si);
+    Vec4Load<R>::st(st + 12, -sth * ci, -(co * cs2 + so * ci), co * ci - so * cs2, sth * si);
   }
   // Staging of one layer (blocks k0 .. k0 + NBL - 1): the sample's lanes split the layer's 2 NBL fused gates.
   // u_in of a block gate is recovered from the merged diagonal: u_in = A conj(pending u_out of the previous gate).
@@ -790,7 +811,10 @@ heis_kernel(const KParams<R> p) {
               reg_part += val;
               rs = mul_rn(p.pen.r, slope);
             }
-            cf[0] = c; cf[1] = s; cf[2] = rs;
+            // CP(a) = CP(a - 2 pi): keep cos(a/2) >= 0, so the ZZ pair rotation of the backward sweep is a rotation
+            // by at most pi/2 and its lifting coefficient t = -tan(a/4) is bounded (phase_bwd)
+            if (c < R(0)) { c = -c; s = -s; }
+            cf[0] = c; cf[1] = s; cf[2] = rs; cf[3] = -s * rcp_fast(R(1) + c);
           }
         }
       }
