@@ -628,17 +628,21 @@ template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, Pk4<R>* pk, int g0,
                                               int g_end, int stride, R* coef, R* aux) {
   constexpr int SW = HEIS_SU2_WORDS;
-  // two gates ahead: the L2 round trip of the packed state is longer than the update of one gate
-  GateIn<R> cur = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
-  GateIn<R> nxt = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride,
-                                 coef + SW * (g0 + stride), aux + 4 * (g0 + stride));
+  // Two gates in flight, loop unrolled by two so that the buffers keep their registers (no copies at the back
+  // edge): the state of gate g + 2 stride is requested as soon as gate g is done and has the whole update of
+  // gate g + stride to arrive (the L2 round trip is about as long as one gate's update).
+  GateIn<R> ga = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
+  GateIn<R> gb = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride,
+                                coef + SW * (g0 + stride), aux + 4 * (g0 + stride));
 #pragma unroll 1
-  for (int g = g0; g < g_end; g += stride) {
-    const int gn = g + 2 * stride;
-    const GateIn<R> nn = heis_gate_load(p, u, pk, gn < g_end, p.su2 + gn, ms + gn, coef + SW * gn, aux + 4 * gn);
-    heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, cur, coef + SW * g, aux + 4 * g);
-    cur = nxt;
-    nxt = nn;
+  for (int g = g0; g < g_end; g += 2 * stride) {
+    heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, ga, coef + SW * g, aux + 4 * g);
+    const int g2 = g + 2 * stride;
+    ga = heis_gate_load(p, u, pk, g2 < g_end, p.su2 + g2, ms + g2, coef + SW * g2, aux + 4 * g2);
+    const int g1 = g + stride;
+    if (g1 < g_end) heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g1, gb, coef + SW * g1, aux + 4 * g1);
+    const int g3 = g + 3 * stride;
+    gb = heis_gate_load(p, u, pk, g3 < g_end, p.su2 + g3, ms + g3, coef + SW * g3, aux + 4 * g3);
   }
 }
 template <typename R>
