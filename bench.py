@@ -372,7 +372,8 @@ def run_b200(args):
     rp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(rp):
         try:
-            traffic = json.load(open(rp)).get("dram_bytes_per_launch")
+            traffic = next((e["dram_bytes_per_launch"] for e in json.load(open(rp))["launches"]
+                            if e["samples"] == B and e["iters"] == T), None)   # ncu capture of this launch shape
         except Exception:
             traffic = None
     roofline = {"bound": "fp32", "kernel": "cpf::heis_kernel<float,4,2,HeisSweep<chain>>",
