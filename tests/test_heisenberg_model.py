@@ -127,3 +127,52 @@ def test_zz_split_of_the_cp_gate():
         l, g = H.grad_hs_zz(n, ops, a, tgt)
         l2, g2 = O.hand_adjoint_grad(n, ops, a, "hs", tgt)
         assert abs(l - l2) < 1e-13 and np.abs(g - g2).max() < 1e-13
+
+
+def test_lifting_form_of_the_rotations():
+    """heis_impl.cuh / engine.cuh ry_lift, zz_quad: three shears with t = -s/(1+c) are the rotation, for every
+    angle the kernel can meet (phi in [0, pi/2] for Ry, |a/2| <= pi/2 for the canonical entangler angle)."""
+    rng = np.random.default_rng(5)
+    for phi in list(rng.uniform(0, math.pi / 2, 20)) + [0.0, math.pi / 2]:
+        c, s = math.cos(phi), math.sin(phi)
+        t, s2 = H.lift_coeffs(c, s)
+        assert -1.0 - 1e-15 <= t <= 0.0
+        a, b = rng.normal(size=2)
+        la, lb = H.lift_rotate(a, b, t, s2)
+        assert abs(la - (c * a - s * b)) < 1e-14 and abs(lb - (s * a + c * b)) < 1e-14
+        assert abs((1.0 + t * s) - c) < 1e-15          # the staging recovers cos as 1 + t s
+    for a in list(rng.uniform(-20, 20, 50)) + [0.0, math.pi, 2 * math.pi, -math.pi]:
+        c, s, t = H.canonical_half_angle(a)
+        assert c >= 0 and abs(t) <= 1.0 + 1e-12
+        # same gate: e^{ia} from the half angle
+        assert abs(complex(c * c - s * s, 2 * c * s) - np.exp(1j * a)) < 1e-13
+        x, y = rng.normal(size=2)
+        lx, ly = H.lift_rotate(x, y, t, s)
+        assert abs(lx - (c * x - s * y)) < 1e-13 and abs(ly - (s * x + c * y)) < 1e-13
+
+
+def test_so3_from_zyz_data_and_staged_rows():
+    """stage_layer / zyz_to_so3: the SO(3) matrix of G Rz(a/2) from (ty, sy, u_out, u_in) equals so3_of of the
+    2x2 matrix, whichever sign the canonical half angle took, and the staged lane rows reproduce M (X, Y, Z)."""
+    rng = np.random.default_rng(6)
+    for _ in range(20):
+        g = H.rot_mat(H.RZ, rng.uniform(0, 7)) @ H.rot_mat(H.RY, rng.uniform(0, 7)) @ H.rot_mat(H.RX, rng.uniform(0, 7))
+        cy, sy, u_in, u_out = H.zyz(g)
+        ty, _ = H.lift_coeffs(cy, sy)
+        a = rng.uniform(-10, 10)
+        c, s, _ = H.canonical_half_angle(a)
+        m, row_iz, row_xy = H.so3_from_zyz(ty, sy, u_out, u_in * complex(c, s))
+        # reference: SO(3) of G Rz(a'/2), a' = a or a - 2 pi (the canonical representative)
+        ah = 2 * math.atan2(s, c)
+        ref = H.so3_of(g @ H.rot_mat(H.RZ, ah / 2)).T
+        assert np.abs(m - ref).max() < 1e-13
+        X, Y, Z, I = rng.normal(size=4)
+        # lane holding (I, Z): e0 = I, e1 = Z; lane holding (X, Y): e0 = X, e1 = Y
+        send_iz = row_iz[0] * I + row_iz[1] * Z
+        send_xy = row_xy[0] * X + row_xy[1] * Y
+        i2 = row_iz[2] * I + row_iz[3] * Z + row_iz[4] * send_xy
+        z2 = row_iz[5] * I + row_iz[6] * Z + row_iz[7] * send_xy
+        x2 = row_xy[2] * X + row_xy[3] * Y + row_xy[4] * send_iz
+        y2 = row_xy[5] * X + row_xy[6] * Y + row_xy[7] * send_iz
+        want = ref @ np.array([X, Y, Z])
+        assert abs(i2 - I) < 1e-14 and np.abs(np.array([x2, y2, z2]) - want).max() < 1e-13

@@ -322,3 +322,43 @@ def grad_hs_zz(n, ops, angles, target):
             h = conj_zz(h, a, n - 1 - q0, n - 1 - q1)
         i = j - 1
     return loss, grad
+
+
+# ---------------------------------------------------------------------------------------------
+# Arithmetic forms of the current kernel (heis_impl.cuh): rotations as three lifting shears, the SO(3)
+# matrix of a fused gate from its ZYZ data, and the canonical half angle of the entangler.
+# ---------------------------------------------------------------------------------------------
+def lift_coeffs(c, s):
+    """(t, s) of the rotation [[c, -s], [s, c]] with c >= 0: a += t b; b += s a; a += t b."""
+    return -s / (1.0 + c), s
+
+
+def lift_rotate(a, b, t, s):
+    a = a + t * b
+    b = b + s * a
+    a = a + t * b
+    return a, b
+
+
+def so3_from_zyz(ty, sy, u_out, u_in_eff):
+    """M = R(G')^T for G' = diag(1, u_out) Ry diag(1, u_in_eff) from the forward data (ty, sy) of the lifting
+    form (cos = 1 + ty sy); u_in_eff = u_in e^{i a/2} carries the gate's share of its CP gate.  Returned in the
+    staged layout: row for (I, Z) lanes, row for (X, Y) lanes (ka, kb, k00, k01, k02, k10, k11, k12)."""
+    cy = 1.0 + ty * sy
+    ct, st = cy * cy - sy * sy, 2.0 * cy * sy
+    co, so = u_out.real, u_out.imag
+    ci, si = u_in_eff.real, u_in_eff.imag
+    m = np.array([[co * ct * ci - so * si, so * ct * ci + co * si, -st * ci],
+                  [-(co * ct * si + so * ci), co * ci - so * ct * si, st * si],
+                  [co * st, so * st, ct]])
+    row_iz = np.array([0.0, 1.0, 1.0, 0.0, 0.0, 0.0, m[2, 2], 1.0])
+    row_xy = np.array([m[2, 0], m[2, 1], m[0, 0], m[0, 1], m[0, 2], m[1, 0], m[1, 1], m[1, 2]])
+    return m, row_iz, row_xy
+
+
+def canonical_half_angle(a):
+    """(c, s, t) of the entangler angle a as the kernel keeps them: c = cos(a/2) >= 0 (CP(a) = CP(a - 2 pi))."""
+    c, s = math.cos(a / 2), math.sin(a / 2)
+    if c < 0:
+        c, s = -c, -s
+    return c, s, -s / (1.0 + c)
