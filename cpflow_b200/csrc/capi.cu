@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <mutex>
 #include <string>
 
 #include "cpflow_b200.h"
@@ -158,6 +159,24 @@ int stage_target(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KPara
   return CPF_OK;
 }
 
+// Per-call scratch (packed optimiser state, staged targets) comes from the device's default stream-ordered pool.
+// Its release threshold defaults to 0: freed blocks go back to the driver at the next synchronisation and the
+// next call pays for mapping hundreds of megabytes again.  Keep them in the pool (once per device and process).
+static void keep_pool_memory() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
+
 // ---- Heisenberg-picture kernels (heis_impl.cuh): HS loss on layered templates ----
 // CPF_ENGINE=adjoint forces the state-adjoint kernels (tests cover both engines).
 template <typename R>
@@ -176,6 +195,7 @@ bool use_heis(const cpf::Program* prog, const cpf_loss_spec* loss) {
 template <typename R>
 int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams<R>& p, R** packed, R** aux,
                cudaStream_t st) {
+  keep_pool_memory();
   const int cpt = cpf::heis_cpt<R>(prog->n_qubits);
   const int words = cpf::heis_target_words<R>(prog->n_qubits, cpt);
   const size_t bytes = ((size_t)words * sizeof(R) + 15) & ~(size_t)15;

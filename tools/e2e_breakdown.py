@@ -13,7 +13,8 @@ T = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 anz = Ansatz(4, "cp", fill_layers(chain_layer(4), 40)); prog = anz.program
 pf = make_regularization_function(RegularizationOptions); pen = Penalty("piecewise", 0.001476, pf.segments, pf.period)
 loss = Loss("hs", u_toff4)
-a0 = prog.initial_angles(0, 12500); a0_host = a0.cpu().pin_memory()
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+a0 = prog.initial_angles(0, B); a0_host = a0.cpu().pin_memory()
 pl = ProgramLoss(prog, loss)
 def sync(): torch.cuda.synchronize(); return time.perf_counter()
 for rep in range(3):
