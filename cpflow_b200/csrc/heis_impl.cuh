@@ -28,20 +28,21 @@
 
 namespace cpf {
 
-// Shared-memory slot of a fused one-qubit gate, 8 words: ty, sy (lifting form of Ry: ty = -sy / (1 + cy)) | u_out | u_in (surface) / A (lower-qubit gate) /
-// A B e^{ia} (higher-qubit gate) | B (lower-qubit gate).  The backward sweep overwrites words 0..2 with the
-// gradient sums (S_X, S_Y, S_Z).  The SO(3) rows of the backward sweep are NOT kept per gate: they are
-// produced one layer at a time in a staging area (HEIS_STAGE_WORDS per gate of a layer), which keeps the
-// per-sample footprint small enough for two co-resident CTAs of 7-8 warps per SM.
+// Shared-memory slot of a fused one-qubit gate, 8 words: ty, sy (lifting form of Ry: ty = -sy / (1 + cy)) | u_out |
+// u_in (surface) / A (lower-qubit gate) / A B e^{ia} (higher-qubit gate) | B (lower-qubit gate) / r * penalty
+// slope of the block's entangler (higher-qubit gate, word 6).  The backward sweep overwrites words 0, 1, 4 with the
+// gradient sums (S_X, S_Y, S_Z); u_out stays (the parameter phase needs it to bring the sums back to the gate's
+// output frame).  The coefficients of the backward sweep are NOT kept per gate: they are produced one layer at a
+// time in a staging area (HEIS_STAGE_WORDS per gate of a layer), which keeps the per-sample footprint small enough
+// for 64 resident samples (16 warps) per SM on C3.
 constexpr int HEIS_SU2_WORDS = 8;
-// Staged coefficients of a gate of the backward sweep, 16 words: two rows (ka, kb, k00, k01 | k02, k10, k11, k12)
-// of the lane-uniform update  send = ka e0 + kb e1;  e0' = k00 e0 + k01 e1 + k02 recv;  e1' = k10 e0 + k11 e1 + k12 recv:
-// row 0 for lanes that hold (I, Z) of the gate's qubit (0, 1, 1, 0 | 0, 0, m22, 1), row 1 for lanes that hold (X, Y)
-// (m20, m21, m00, m01 | m02, m10, m11, m12), M = R(G)^T.  A lane picks its row by address: no selects.
-constexpr int HEIS_STAGE_WORDS = 16;
+// Staged coefficients of a gate of the backward sweep (Z-X-Z form, see backward()), 8 words: two rows
+// (cos theta, -+sin theta, cos zeta | 1, sin zeta | 0): row 0 for lanes that hold (I, Z) of the gate's qubit, row 1
+// for lanes that hold (X, Y).  A lane picks its row by address: no selects.
+constexpr int HEIS_STAGE_WORDS = 8;
 constexpr int HEIS_SYNC_EVERY_DEFAULT = 1 << 20;   // layers between CTA barriers inside a sweep (first layer always)
 constexpr int HEIS_SKEW_DEFAULT = 0;    // % of a CTA's warps in phase group A (heis_kernel); 0 = unskewed
-constexpr int HEIS_CP_WORDS = 4;     // cos(a/2) >= 0, sin(a/2), r * penalty slope, -tan(a/4); word 0 <- dL/da after the backward sweep
+constexpr int HEIS_CP_WORDS = 3;     // cos(a/2) >= 0, sin(a/2), -tan(a/4); word 0 <- dL/da after the backward sweep
 
 inline int heis_coef_stride(int n_su2, int n_cp, int n_stage) {
   int w = (HEIS_SU2_WORDS * n_su2 + HEIS_CP_WORDS * n_cp + HEIS_STAGE_WORDS * n_stage + 3) & ~3;
@@ -220,25 +221,32 @@ struct HeisSweep {
   // ------------------------------- backward: real maps on h -------------------------------
   // h[xr][z] is held packed over xr: hv[z] = (h[0][z], h[1][z]) for CPT = 2 (scalar for CPT = 1), so every map
   // whose coefficients do not depend on xr issues as FFMA2; only gates on amplitude bit 0 (x bit = xr) are scalar.
-  // Fused one-qubit gate on amplitude bit B.  cf: rows of M = R(G)^T in the staging area, (X', Y', Z') = M (X, Y, Z),
-  // each row padded to 4 words; words 0..2 of the gate's slot receive the gradient sums (S_X, S_Y, S_Z) = entries of h.
+  //
+  // Z-X-Z form with merged Rz factors (tools/heisenberg_model.py: grad_hs_zxz).  G ~ Rz(phi_out) Ry(theta) Rz(phi_in)
+  // = Rz(phi_out + pi/2) Rx(theta) Rz(phi_in - pi/2).  Rx mixes (Y, Z): for a lane-bit qubit both sit in register
+  // slot z | BM of the two paired lanes, so the exchange is the raw register (no send computation): 2 FMA + SHFL per
+  // packed pair; Rz mixes (X, Y), which one lane holds: 4 FMA.  Everything between the Rx of consecutive gates on
+  // a qubit is Z-type and commutes, so a gate's outgoing Rz is undone together with the incoming Rz of the NEXT
+  // gate on that qubit: per gate, undo Rx(theta), then Rz(zeta) with e^{i zeta} = (A or B of the forward sweep's
+  // merged diagonal) e^{i a/2}.  6 instead of 8 packed instructions per pair, and nothing to select.
+  // cf: the gate's staged rows; words 0, 1, 4 of the gate's slot sl receive (S_X, S_Y, S_Z) = entries of h in the
+  // frame where the gate's own Rz(phi_out + pi/2) is already undone (the parameter phase rotates them back).
   template <int B>
   static __device__ __forceinline__ void su2_bwd(V (&hv)[N], const R* cf, R* sl, int m) {
     constexpr int BM = 1 << B;
     if constexpr (B < PB) {
       const bool own = m == 0;
-      sts_if(own, sl, T::get(hv[0], 1)); sts_if(own, sl + 1, T::get(hv[BM], 1)); sts_if(own, sl + 2, T::get(hv[BM], 0));
+      sts_if(own, sl, T::get(hv[0], 1)); sts_if(own, sl + 1, T::get(hv[BM], 1)); sts_if(own, sl + 4, T::get(hv[BM], 0));
       // x bit = xr: I = h[0][z], Z = h[0][z|1], X = h[1][z], Y = h[1][z|1]
-      R m20, m21, m00, m01, m02, m10, m11, m12;
-      Vec4Load<R>::ld(cf + 8, m20, m21, m00, m01);
-      Vec4Load<R>::ld(cf + 12, m02, m10, m11, m12);
-      const R m22 = cf[6];
+      R ct, st, cz, sz;
+      Vec4Load<R>::ld(cf + 4, ct, st, cz, sz);
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & BM) continue;
         const R X = T::get(hv[z], 1), Y = T::get(hv[z | BM], 1), Z = T::get(hv[z | BM], 0);
-        hv[z] = T::make(T::get(hv[z], 0), m00 * X + m01 * Y + m02 * Z);
-        hv[z | BM] = T::make(m20 * X + m21 * Y + m22 * Z, m10 * X + m11 * Y + m12 * Z);
+        const R Y1 = ct * Y + st * Z;
+        hv[z] = T::make(T::get(hv[z], 0), cz * X + sz * Y1);
+        hv[z | BM] = T::make(ct * Z - st * Y, cz * Y1 - sz * X);
       }
     } else {
       // x bit is lane bit J: lanes with the bit clear hold (I, Z), lanes with it set hold (X, Y)
@@ -246,21 +254,42 @@ struct HeisSweep {
       const bool mb = ((m >> J) & 1) != 0;
       const bool own = m == (1 << J);
       sts_if(own, sl, T::get(hv[0], 0)); sts_if(own, sl + 1, T::get(hv[BM], 0));
-      sts_if(m == 0, sl + 2, T::get(hv[BM], 0));
-      const R* row = cf + (mb ? 8 : 0);
-      R a, b, c00, c01, c02, c10, c11, c12;
-      Vec4Load<R>::ld(row, a, b, c00, c01);
-      Vec4Load<R>::ld(row + 4, c02, c10, c11, c12);
-      const V ka = T::bc(a), kb = T::bc(b), k00 = T::bc(c00), k01 = T::bc(c01), k02 = T::bc(c02), k10 = T::bc(c10),
-              k11 = T::bc(c11), k12 = T::bc(c12);
+      sts_if(m == 0, sl + 4, T::get(hv[BM], 0));
+      R ct, st, cz, sz;
+      Vec4Load<R>::ld(cf + (mb ? 4 : 0), ct, st, cz, sz);
+      const V kct = T::bc(ct), kst = T::bc(st), kcz = T::bc(cz), ksz = T::bc(sz), knz = T::bc(-sz);
+#pragma unroll
+      for (int z = 0; z < N; ++z) {
+        if (z & BM) continue;
+        const V recv = ShflV<V>::x(hv[z | BM], 1 << J);
+        const V e1 = T::fma(kst, recv, T::mul(kct, hv[z | BM]));   // (X, Y) lanes: Y' = ct Y + st Z; (I, Z): Z' = ct Z - st Y
+        const V e0 = hv[z];
+        hv[z] = T::fma(ksz, e1, T::mul(kcz, e0));                  // X' = cz X + sz Y'      (identity on (I, Z) lanes)
+        hv[z | BM] = T::fma(knz, e0, T::mul(kcz, e1));             // Y'' = cz Y' - sz X
+      }
+    }
+  }
+  // Rz alone (the outgoing Rz of the last gate on a qubit, undone before the sweep starts): (X, Y) -> (c X + s Y, c Y - s X)
+  template <int B>
+  static __device__ __forceinline__ void rz_bwd(V (&hv)[N], R c, R s, int m) {
+    constexpr int BM = 1 << B;
+    if constexpr (B < PB) {
+#pragma unroll
+      for (int z = 0; z < N; ++z) {
+        if (z & BM) continue;
+        const R X = T::get(hv[z], 1), Y = T::get(hv[z | BM], 1);
+        hv[z] = T::make(T::get(hv[z], 0), c * X + s * Y);
+        hv[z | BM] = T::make(T::get(hv[z | BM], 0), c * Y - s * X);
+      }
+    } else {
+      const bool mb = ((m >> (B - PB)) & 1) != 0;
+      const V kc = T::bc(mb ? c : R(1)), ks = T::bc(mb ? s : R(0)), kn = T::bc(mb ? -s : R(0));
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & BM) continue;
         const V e0 = hv[z], e1 = hv[z | BM];
-        const V send = T::fma(kb, e1, T::mul(ka, e0));
-        const V recv = ShflV<V>::x(send, 1 << J);
-        hv[z] = T::fma(k02, recv, T::fma(k01, e1, T::mul(k00, e0)));
-        hv[z | BM] = T::fma(k12, recv, T::fma(k11, e1, T::mul(k10, e0)));
+        hv[z] = T::fma(ks, e1, T::mul(kc, e0));
+        hv[z | BM] = T::fma(kn, e0, T::mul(kc, e1));
       }
     }
   }
@@ -286,7 +315,7 @@ struct HeisSweep {
   template <int B1, int B2>
   static __device__ __forceinline__ void phase_bwd(V (&hv)[N], R* cf, int m) {
     constexpr int M1 = 1 << B1, M2 = 1 << B2;
-    const R s = cf[1], t = cf[3];
+    const R s = cf[1], t = cf[2];
     const R g11 = R(-0.5) * ((T::get(hv[0], 0) - T::get(hv[M1], 0)) - (T::get(hv[M2], 0) - T::get(hv[M1 | M2], 0)));
     __syncwarp();
     sts_if(m == 0, cf, g11);
@@ -343,56 +372,54 @@ struct HeisSweep {
       surface_bwd<Q - 1>(coef, stage, m, h);
     }
   }
-  // SO(3) rows of G' = diag(1, u_out) Ry diag(1, u_in') = Rz3(phi_out) Ry3(theta) Rz3(phi_in'), stored transposed
-  // (M = R^T) in rows of 4 words.  (ci, si) = u_in' = u_in e^{i a/2} carries the block's share of its CP gate.
-  static __device__ __forceinline__ void zyz_to_so3(R* st, R ty, R sy, R co, R so, R ci, R si) {
+  // Staged rows of one gate: Rx angle from the forward data (cos phi = 1 + ty sy, theta = 2 phi), Rz angle zeta.
+  static __device__ __forceinline__ void stage_gate(R* st, R ty, R sy, R cz, R sz) {
     const R cy = R(1) + ty * sy;   // 1 - tan(phi/2) sin phi = cos phi
     const R ct = cy * cy - sy * sy, sth = R(2) * cy * sy;
-    const R cc = ct * ci, cs2 = ct * si;
-    // rows of M = R^T: (m00 m01 m02) = (co cc - so si, so cc + co si, -sth ci), (m10 m11 m12) =
-    // (-(co cs2 + so ci), co ci - so cs2, sth si), (m20 m21 m22) = (co sth, so sth, ct)
-    Vec4Load<R>::st(st, R(0), R(1), R(1), R(0));
-    Vec4Load<R>::st(st + 4, R(0), R(0), ct, R(1));
-    Vec4Load<R>::st(st + 8, co * sth, so * sth, co * cc - so * si, so * cc + co * si);
-    Vec4Load<R>::st(st + 12, -sth * ci, -(co * cs2 + so * ci), co * ci - so * cs2, sth * si);
+    Vec4Load<R>::st(st, ct, -sth, R(1), R(0));
+    Vec4Load<R>::st(st + 4, ct, sth, cz, sz);
   }
   // Staging of one layer (blocks k0 .. k0 + NBL - 1): the sample's lanes split the layer's 2 NBL fused gates.
-  // u_in of a block gate is recovered from the merged diagonal: u_in = A conj(pending u_out of the previous gate).
-  static __device__ __forceinline__ void stage_layer(const HCp* mcp, int k0, int K, const R* coef, const R* cph0,
-                                                     R* stage, int m) {
+  // e^{i zeta} = d e^{i a/2}, d = A (lower-qubit gate) / B (higher-qubit gate) of the forward sweep's merged diagonal.
+  static __device__ __forceinline__ void stage_layer(int k0, int K, const R* coef, const R* cph0, R* stage, int m) {
     const int nb = K - k0 < NBL ? K - k0 : NBL;
 #pragma unroll 1
     for (int j = m; j < 2 * nb; j += TPS) {
       const int k = k0 + (j >> 1), hi = j & 1;
-      const HCp md = mcp[k];
       const R* cl = coef + SW * (NQ + 2 * k);
       const R* cf = cl + SW * hi;
-      const R* pv = coef + SW * (hi ? md.prev_hi : md.prev_lo);
       const R* cc = cph0 + CW * k;
-      const R dr = cl[4 + 2 * hi], di = cl[5 + 2 * hi];          // A (lower-qubit gate) / B (higher-qubit gate)
-      const R pr = pv[2], pi = pv[3];
-      const R ur = dr * pr + di * pi, ui = di * pr - dr * pi;    // u_in = d conj(pend)
+      const R dr = cl[4 + 2 * hi], di = cl[5 + 2 * hi];
       const R ch = cc[0], sh = cc[1];
-      zyz_to_so3(stage + STW * j, cf[0], cf[1], cf[2], cf[3], ur * ch - ui * sh, ur * sh + ui * ch);
+      stage_gate(stage + STW * j, cf[0], cf[1], dr * ch - di * sh, dr * sh + di * ch);
     }
   }
+  // surface gates: zeta = phi_in - pi/2
   static __device__ __forceinline__ void stage_surface(const R* coef, R* stage, int m) {
 #pragma unroll 1
     for (int q = m; q < NQ; q += TPS) {
       const R* cf = coef + SW * q;
-      zyz_to_so3(stage + STW * q, cf[0], cf[1], cf[2], cf[3], cf[4], cf[5]);
+      stage_gate(stage + STW * q, cf[0], cf[1], cf[5], -cf[4]);
     }
   }
-  static __device__ __forceinline__ void backward(const KParams<R>& p, const HCp* mcp, const LayerBar lb, R* coef,
-                                                  R* stage, int m, V (&h)[N]) {
+  template <int Q>
+  static __device__ __forceinline__ void tail_bwd(const KParams<R>& p, const R* coef, int m, V (&h)[N]) {
+    if constexpr (Q < NQ) {
+      const R* cf = coef + SW * p.last_slot[Q];
+      rz_bwd<NQ - 1 - Q>(h, -cf[3], cf[2], m);     // Rz(phi_out + pi/2): e^{i w} = i u_out
+      tail_bwd<Q + 1>(p, coef, m, h);
+    }
+  }
+  static __device__ __forceinline__ void backward(const KParams<R>& p, const LayerBar lb, R* coef, R* stage, R* cph0,
+                                                  int m, V (&h)[N]) {
     const int K = p.n_cp;
-    R* cph0 = coef + SW * p.n_su2;
-#pragma unroll 1
+    tail_bwd<0>(p, coef, m, h);
     int li = 0;
+#pragma unroll 1
     for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL) {
       if (li == 0 && lb.every_bwd > 0) lb.sync();
       li = li + 1 == lb.every_bwd ? 0 : li + 1;
-      stage_layer(mcp, k0, K, coef, cph0, stage, m);
+      stage_layer(k0, K, coef, cph0, stage, m);
       __syncwarp();
       blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
       __syncwarp();
@@ -568,7 +595,10 @@ __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const U
   if (in.pi1 >= 0) in.v1 = pk_load(pk + in.pi1); else in.v1.th = R(md->cangle[1]);
   if (in.pi2 >= 0) in.v2 = pk_load(pk + in.pi2); else in.v2.th = R(md->cangle[2]);
   if (u.phase != PH_COEF) {
-    in.sx = cf[0]; in.sy = cf[1]; in.sz = cf[2];
+    // gradient sums of the backward sweep, back to the gate's output frame: the sweep reads them after the gate's
+    // own Rz(phi_out + pi/2) is undone, e^{i w} = i u_out (u_out is still in words 2, 3 from the last update)
+    const R px = cf[0], py = cf[1], wr = -cf[3], wi = cf[2];
+    in.sx = wr * px - wi * py; in.sy = wi * px + wr * py; in.sz = cf[4];
     Vec4Load<R>::ld(ax, in.c2, in.s2, in.c3, in.s3);
   }
   return in;
@@ -719,7 +749,8 @@ heis_kernel(const KParams<R> p) {
   const int P = p.P;
   // idle sample slots (block size rounded up to whole warps) replay sample B-1 in one spare store
   R* coef = s_coef + (size_t)(sl < p.spb ? sl : p.spb) * p.coef_stride;
-  R* coef_cp = coef + SW * p.n_su2;
+  R* stage = coef + SW * p.n_su2;                          // staged rows of one layer of the backward sweep
+  R* coef_cp = stage + HEIS_STAGE_WORDS * SWP::NSTAGE;
   const V* tv = reinterpret_cast<const V*>(s_target) + 2 * (size_t)m * (N + 1);
 
   const unsigned off = (unsigned)(b * P);   // host: B * P < 2^32
@@ -798,9 +829,10 @@ heis_kernel(const KParams<R> p) {
           if (kn < p.n_cp) { md_n = s_cp[kn]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
           const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 && (md.flags & 1) != 0;
           if (pi < 0) v.th = R(p.cp[k].cangle);
-          // cf[0]: dL/da from the sweep; cf[2]: r * penalty slope at this angle (stored with the coefficients)
+          // cf[0]: dL/da from the sweep; word 6 of the block's higher-qubit gate slot: r * penalty slope at this angle
+          R* rsw = coef + SW * (NQ + 2 * k + 1) + 6;
           if (phase != PH_COEF && pi >= 0) {
-            const R g = add_rn(cf[0], cf[2]);
+            const R g = add_rn(cf[0], *rsw);
             if (plain) heis_apply<R, true>(p, u, pk, pi, g, v);
             else heis_apply<R, false>(p, u, pk, pi, g, v);
           }
@@ -818,7 +850,7 @@ heis_kernel(const KParams<R> p) {
             // CP(a) = CP(a - 2 pi): keep cos(a/2) >= 0, so the ZZ pair rotation of the backward sweep is a rotation
             // by at most pi/2 and its lifting coefficient t = -tan(a/4) is bounded (phase_bwd)
             if (c < R(0)) { c = -c; s = -s; }
-            cf[0] = c; cf[1] = s; cf[2] = rs; cf[3] = -s * rcp_fast(R(1) + c);
+            cf[0] = c; cf[1] = s; cf[2] = -s * rcp_fast(R(1) + c); *rsw = rs;
           }
         }
       }
@@ -904,7 +936,7 @@ heis_kernel(const KParams<R> p) {
     __syncwarp();
 
     // ---------------- Heisenberg sweep ----------------
-    SWP::backward(p, s_cp, lb, coef, coef_cp + CW * p.n_cp, m, h);
+    SWP::backward(p, lb, coef, stage, coef_cp, m, h);
     __syncwarp();
     if (skew) cta_sync();
   }

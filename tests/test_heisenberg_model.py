@@ -176,3 +176,22 @@ def test_so3_from_zyz_data_and_staged_rows():
         y2 = row_xy[5] * X + row_xy[6] * Y + row_xy[7] * send_iz
         want = ref @ np.array([X, Y, Z])
         assert abs(i2 - I) < 1e-14 and np.abs(np.array([x2, y2, z2]) - want).max() < 1e-13
+
+
+@pytest.mark.parametrize("n,layer,K,rg,ent", [(3, O.chain_layer(3), 5, "xyz", "cp"), (4, O.chain_layer(4), 7, "xyz", "cp"),
+                                              (4, [[0, 1], [0, 2], [0, 3]], 4, "xz", "cp"),
+                                              (3, O.connected_layer(3), 6, "zyx", "cp"), (2, [[0, 1]], 3, "xyz", "cp"),
+                                              (3, O.chain_layer(3), 4, "xyz", "cz")])
+def test_merged_zxz_backward_sweep(n, layer, K, rg, ent):
+    """The kernel's backward sweep: Rx / merged-Rz undo per gate, gradient sums in the rotated frame, frame change
+    and chain rule of the parameter phase: equals the oracle gradient."""
+    rng = np.random.default_rng(K + 11)
+    anz = O.cp_ansatz(layer, K, rg)
+    ops = O.ansatz_program(anz)
+    if ent == "cz":      # CZ entanglers (projected CP gates): no parameter, a = pi exactly
+        ops = [(H.CZ, q0, q1, -1, 0.0) if kind == H.CP else (kind, q0, q1, pi, c) for kind, q0, q1, pi, c in ops]
+    tgt = unitary_group.rvs(1 << n, random_state=4)
+    a = rng.uniform(-2 * np.pi, 4 * np.pi, anz.num_angles)
+    l, g = H.grad_hs_zxz(n, ops, a, tgt)
+    l2, g2 = O.hand_adjoint_grad(n, ops, a, "hs", tgt)
+    assert abs(l - l2) < 1e-13 and np.abs(g - g2).max() < 1e-12

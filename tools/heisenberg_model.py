@@ -362,3 +362,126 @@ def canonical_half_angle(a):
     if c < 0:
         c, s = -c, -s
     return c, s, -s / (1.0 + c)
+
+
+# ---------------------------------------------------------------------------------------------
+# Backward sweep in Z-X-Z form with the Rz factors merged across the entanglers (heis_impl.cuh: backward).
+# G ~ Rz(phi_out) Ry(theta) Rz(phi_in) = Rz(phi_out + pi/2) Rx(theta) Rz(phi_in - pi/2).  In the Pauli basis Rx
+# mixes (Y, Z): for a qubit whose x bit is a lane bit both sit in the SAME register slot of the two paired lanes, so
+# the exchange needs no send computation (2 FMA + 1 SHFL per pair); Rz mixes (X, Y), which one lane holds (4 FMA).
+# Everything between the Rx of consecutive gates on a qubit is Z-type (Rz factors, CP halves, ZZ rotations) and
+# commutes, so the outgoing Rz of a gate is undone together with the incoming Rz of the NEXT gate on that qubit:
+#   per gate: undo Rx(theta), then undo Rz(zeta), e^{i zeta} = pending u_out(prev) * u_in * e^{i a/2}
+# (= the forward sweep's merged diagonal A or B times the entangler's half angle; the +-pi/2 cancel).  The gradient
+# sums are read in the frame where the gate's own outgoing Rz(phi_out + pi/2) is already undone; the parameter
+# phase rotates (S_X, S_Y) back with u_out.
+# ---------------------------------------------------------------------------------------------
+def layered_gates(n, ops, angles):
+    """Fused gates in kernel slot order (surface gate of qubit q: slot q; block k: lower-qubit gate slot n + 2k,
+    higher-qubit gate n + 2k + 1), each a list of (kind, pidx, angle) in time order, and the blocks
+    [(lo, hi, kind, pidx, angle)]."""
+    gates = {q: [] for q in range(n)}
+    blocks = []
+    for kind, q0, q1, pi, const in ops:
+        a = angles[pi] if pi >= 0 else const
+        if kind in (RX, RY, RZ):
+            if not blocks:
+                gates[q0].append((kind, pi, a))
+            else:
+                lo, hi = blocks[-1][0], blocks[-1][1]
+                k = len(blocks) - 1
+                gates.setdefault(n + 2 * k + (0 if q0 == lo else 1), []).append((kind, pi, a))
+        else:
+            k = len(blocks)
+            blocks.append((min(q0, q1), max(q0, q1), kind, pi, a if kind == CP else math.pi))
+            gates[n + 2 * k] = []
+            gates[n + 2 * k + 1] = []
+    return [gates[s] for s in range(n + 2 * len(blocks))], blocks
+
+
+def rz_undo(h, u, bit):
+    """h <- coefficients of Rz(zeta)^dag H Rz(zeta), e^{i zeta} = u: (X, Y) -> (c X + s Y, -s X + c Y)."""
+    N = h.shape[0]
+    b = 1 << bit
+    c, s = u.real, u.imag
+    out = h.copy()
+    for x in range(N):
+        if x & b:
+            continue
+        for z in range(N):
+            if z & b:
+                continue
+            X, Y = h[x | b, z], h[x | b, z | b]
+            out[x | b, z], out[x | b, z | b] = c * X + s * Y, -s * X + c * Y
+    return out
+
+
+def rx_undo(h, ct, st, bit):
+    """h <- coefficients of Rx(theta)^dag H Rx(theta): (Y, Z) -> (ct Y + st Z, -st Y + ct Z)."""
+    N = h.shape[0]
+    b = 1 << bit
+    out = h.copy()
+    for x in range(N):
+        if x & b:
+            continue
+        for z in range(N):
+            if z & b:
+                continue
+            Y, Z = h[x | b, z | b], h[x, z | b]
+            out[x | b, z | b], out[x, z | b] = ct * Y + st * Z, -st * Y + ct * Z
+    return out
+
+
+def grad_hs_zxz(n, ops, angles, target):
+    """(loss, grad[P]) through the merged Z-X-Z backward sweep, including the parameter phase's frame change of the
+    gradient sums and its chain rule through the fused rotations."""
+    N = 1 << n
+    gates, blocks = layered_gates(n, ops, angles)
+    y = forward_merged(n, ops, angles, target)
+    t, h = to_pauli(y)
+    loss = 1 - abs(t) ** 2 / N ** 2
+
+    def fuse(seq):
+        g = np.eye(2, dtype=complex)
+        for kind, _, a in seq:
+            g = rot_mat(kind, a) @ g
+        return g
+    data = [zyz(fuse(g)) for g in gates]               # cy, sy, u_in, u_out
+    qubit_of = list(range(n)) + [q for lo, hi, *_ in blocks for q in (lo, hi)]
+    prev, last = {}, {q: q for q in range(n)}
+    for s in range(n, len(gates)):
+        prev[s] = last[qubit_of[s]]
+        last[qubit_of[s]] = s
+    bit = lambda q: n - 1 - q
+    for q in range(n):                                   # tail: the outgoing Rz of the last gate on every qubit
+        h = rz_undo(h, data[last[q]][3] * 1j, bit(q))
+    S = {}
+    grad = np.zeros(len(angles))
+
+    def undo_gate(h, s, u_in_eff):
+        b = 1 << bit(qubit_of[s])
+        S[s] = np.array([h[b, 0], h[b, b], h[0, b]])
+        cy, sy = data[s][0], data[s][1]
+        h = rx_undo(h, cy * cy - sy * sy, 2 * cy * sy, bit(qubit_of[s]))
+        return rz_undo(h, u_in_eff, bit(qubit_of[s]))
+    for k in reversed(range(len(blocks))):
+        lo, hi, kind, pi, a = blocks[k]
+        c, s_, _ = canonical_half_angle(a)
+        for s in (n + 2 * k + 1, n + 2 * k):
+            h = undo_gate(h, s, data[prev[s]][3] * data[s][2] * complex(c, s_))
+        b1, b2 = 1 << bit(lo), 1 << bit(hi)
+        if kind == CP and pi >= 0:
+            grad[pi] += -0.5 * (h[0, 0] - h[0, b1] - h[0, b2] + h[0, b1 | b2])
+        h = conj_zz(h, 2 * math.atan2(s_, c), bit(lo), bit(hi))
+    for q in reversed(range(n)):
+        h = undo_gate(h, q, data[q][2] * (-1j))
+    # parameter phase: back to the gate's output frame, then the chain rule through G = R_2 R_1 R_0
+    for s, seq in enumerate(gates):
+        w = data[s][3] * 1j
+        sx, sy, sz = S[s]
+        vec = np.array([w.real * sx - w.imag * sy, w.imag * sx + w.real * sy, sz])
+        for kind, pi, a in reversed(seq):
+            if pi >= 0:
+                grad[pi] += vec[{RX: 0, RY: 1, RZ: 2}[kind]]
+            vec = so3_of(rot_mat(kind, a)).T @ vec
+    return loss, grad
