@@ -972,31 +972,59 @@ __global__ void pack_target_heis_kernel(const R* __restrict__ src, R* __restrict
 
 // Launch geometry: spread the batch evenly over SMs and rounds so that the last wave is as full as the
 // first (every CTA runs all the Adam steps of its samples, so a ragged last wave costs a whole wave).
-//   ctas  resident CTAs per SM (independent instruction streams; default 1: one synchronised stream shares the instruction cache; env CPF_HEIS_CTAS)
-//   cap   samples per CTA allowed by shared memory, the thread limit and CPF_HEIS_WARPS
-struct HeisGeometry { int block, spb; long long grid; size_t smem; };
-inline HeisGeometry heis_geometry(long long B, size_t target_bytes, size_t per_sample, int tps, int maxt) {
+//   ctas  resident CTAs per SM.  Each CTA is one synchronised instruction stream (its warps share the instruction
+//         cache); two streams per SM overlap their phases (+4 % on C3 when both hold 8 warps) as long as the SM
+//         keeps as many samples resident as with one: chosen automatically, env CPF_HEIS_CTAS overrides.
+//   cap   samples per CTA allowed by shared memory, the register file, the thread limit and CPF_HEIS_WARPS
+struct HeisGeometry { int block, spb, ctas; long long grid; size_t smem; };
+inline long long heis_cap(int ctas, size_t fixed_bytes, size_t per_sample, int tps, int maxt, int regs, int warps_env) {
+  // registers: allocated per warp in units of 256, 64 K per SM
+  const int regs_warp = ((regs > 0 ? regs : 128) * 32 + 255) / 256 * 256;
+  int warps = 65536 / regs_warp / ctas;
+  if (warps > maxt / 32) warps = maxt / 32;
+  if (warps_env > 0 && warps > warps_env) warps = warps_env;
+  const long long cap_thr = (long long)warps * 32 / tps;
+  const long long smem_cta = (long long)(227 * 1024) / ctas - 1024 - (long long)fixed_bytes;
+  long long cap = smem_cta > 0 ? smem_cta / (long long)per_sample : 0;
+  // a block whose last warp is only partly used parks the idle lanes on one spare slot
+  if (cap > 0 && (cap * tps) % 32 != 0 && cap <= cap_thr) cap -= 1;
+  if (cap > cap_thr) cap = cap_thr;
+  return cap < 1 ? 1 : cap;
+}
+inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sample, int tps, int maxt, int regs) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  int ctas = 1, warps_max = maxt / 32;
+  int ctas = 0, warps_env = 0;
   if (const char* e = getenv("CPF_HEIS_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctas = v; }
-  if (const char* e = getenv("CPF_HEIS_WARPS")) { int v = atoi(e); if (v >= 1 && v <= warps_max) warps_max = v; }
-  const long long smem_cta = (long long)(227 * 1024) / ctas - 1024 - (long long)target_bytes - (long long)per_sample;
-  long long cap = smem_cta > 0 ? smem_cta / (long long)per_sample : 0;   // one spare slot for idle lanes
-  const long long cap_thr = (long long)warps_max * 32 / tps;
-  if (cap > cap_thr) cap = cap_thr;
-  if (cap < 1) cap = 1;
-  const long long slots = (long long)n_sm * ctas;
-  const long long rounds = (B + slots * cap - 1) / (slots * cap);
-  long long spb = (B + slots * rounds - 1) / (slots * rounds);
-  if (spb > cap) spb = cap;
-  if (spb < 1) spb = 1;
+  if (const char* e = getenv("CPF_HEIS_WARPS")) { int v = atoi(e); if (v >= 1) warps_env = v; }
+  const long long slots1 = n_sm;
+  auto spread = [&](int nc, long long& spb_out) {
+    const long long cap = heis_cap(nc, fixed_bytes, per_sample, tps, maxt, regs, warps_env);
+    const long long slots = slots1 * nc;
+    const long long rounds = (B + slots * cap - 1) / (slots * cap);
+    long long spb = (B + slots * rounds - 1) / (slots * rounds);
+    if (spb > cap) spb = cap;
+    if (spb < 1) spb = 1;
+    spb_out = spb;
+    return cap;
+  };
+  long long spb = 1;
+  if (ctas == 0) {
+    // measured on B200: two streams of 8 warps beat one of 16 (+4 % C3, +29 % 5 qubits), two of 6 lose to one of 11
+    long long spb1, spb2;
+    const long long c1 = spread(1, spb1), c2 = spread(2, spb2);
+    ctas = 2 * c2 >= c1 && (spb2 * tps + 31) / 32 >= 8 ? 2 : 1;
+    spb = ctas == 2 ? spb2 : spb1;
+  } else {
+    spread(ctas, spb);
+  }
   HeisGeometry g;
   g.spb = (int)spb;
+  g.ctas = ctas;
   g.block = (int)((spb * tps + 31) / 32 * 32);
   g.grid = (B + spb - 1) / spb;
-  g.smem = target_bytes + (size_t)(spb + 1) * per_sample;
+  g.smem = fixed_bytes + (size_t)(spb + (g.block > spb * tps ? 1 : 0)) * per_sample;
   return g;
 }
 
@@ -1006,8 +1034,14 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   p.n_sched = 0; p.n_red = 0;
   p.coef_stride = heis_coef_stride(p.n_su2, p.n_cp, SWP::NSTAGE);
   if (p.P > 32767) { err = "heis kernel: more than 32767 parameters"; return CPF_ERR_UNSUPPORTED; }
+  auto kern = heis_kernel<R, NQ, CPT, SWP>;
+  static int regs = 0;      // per instantiation
+  if (regs == 0) {
+    cudaFuncAttributes fa;
+    regs = cudaFuncGetAttributes(&fa, kern) == cudaSuccess ? fa.numRegs : 128;
+  }
   const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes + heis_meta_bytes(p.n_su2, p.n_cp),
-                                       (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT);
+                                       (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT, regs);
   p.spb = g.spb;
   // CTA barriers inside the sweeps (they keep the warps on the same instruction-cache lines): one at the start
   // of each sweep is enough to stop the warps drifting apart; a barrier per layer costs 7 % (B200, C3)
@@ -1031,9 +1065,9 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
     err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
     return CPF_ERR_UNSUPPORTED;
   }
-  auto kern = heis_kernel<R, NQ, CPT, SWP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (g.grid <= 0) return CPF_OK;
   if (g.grid > 2147483647LL) { err = "batch too large for one launch"; return CPF_ERR_UNSUPPORTED; }
   kern<<<(unsigned)g.grid, g.block, g.smem, st>>>(p);
