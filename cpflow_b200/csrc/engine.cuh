@@ -63,7 +63,6 @@ struct KParams {
   int coef_stride;  // R words per sample in shared memory
   int spb;          // heis_kernel: sample slots used per CTA
   int sync_every, sync_every_bwd;   // heis_kernel: CTA barrier at every n-th layer of the forward / backward sweep
-  int skew_split;   // heis_kernel: threads in phase group A (multiple of 32); 0 = all warps in phase
   int colmode;      // engine_kernel<SINGLE>, M_UNITARY: virtual sample b = (sample b / N, column b % N)
   int axp_surface, axp_block;   // heis_kernel: packed rotation axes shared by the surface / block gates
   int last_slot[8];             // heis_kernel: slot of the last fused gate on each qubit

@@ -41,7 +41,6 @@ constexpr int HEIS_SU2_WORDS = 8;
 // for lanes that hold (X, Y).  A lane picks its row by address: no selects.
 constexpr int HEIS_STAGE_WORDS = 8;
 constexpr int HEIS_SYNC_EVERY_DEFAULT = 1 << 20;   // layers between CTA barriers inside a sweep (first layer always)
-constexpr int HEIS_SKEW_DEFAULT = 0;    // % of a CTA's warps in phase group A (heis_kernel); 0 = unskewed
 constexpr int HEIS_CP_WORDS = 3;     // cos(a/2) >= 0, sin(a/2), -tan(a/4); word 0 <- dL/da after the backward sweep
 
 inline int heis_coef_stride(int n_su2, int n_cp, int n_stage) {
@@ -68,24 +67,17 @@ struct HCfg {
   static constexpr int PB = CPT == 2 ? 1 : 0;   // x bits of a thread held in registers
   static constexpr int XR = 1 << PB;
   static constexpr int TPS = N / CPT;           // threads per sample
-  // forward state registers: 2 * N * CPT words (x2 for double) -> register cap 168 (384 threads) or 255
+  // forward state registers: 2 * N * CPT words (x2 for double) -> register cap 128 (512 threads) or 255 (256)
   static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? 512 : 256;
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
 };
 
-// Barrier that keeps the warps of one phase group on the same instruction-cache lines.  Unskewed launch:
-// id 0 over the whole CTA (== __syncthreads()); skewed launch (heis_kernel): one named barrier per group.
+// CTA barriers inside the sweeps keep the warps of a CTA on the same instruction-cache lines: one at every
+// `every`-th layer of the forward / backward sweep, counted from the first (0 = never).
 struct LayerBar {
-  int id, cnt, every, every_bwd;   // barrier at every `every`-th layer of the forward / backward sweep (0 = never)
-  __device__ __forceinline__ void sync() const {   // immediate ids: a register id makes ptxas reserve all 16 barriers
-    if (id == 0) asm volatile("bar.sync 0, %0;" ::"r"(cnt) : "memory");
-    else if (id == 1) asm volatile("bar.sync 1, %0;" ::"r"(cnt) : "memory");
-    else asm volatile("bar.sync 2, %0;" ::"r"(cnt) : "memory");
-  }
+  int every, every_bwd;
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
-
-// CTA-wide barrier reached from different code positions by the two phase groups (plain bar.sync 0)
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 // Store to shared memory under a predicate, without a branch (the compiler turns `if (lane == k) s[i] = v`
 // into BSSY / BRA / BSYNC sequences inside the sweeps).
@@ -771,17 +763,8 @@ heis_kernel(const KParams<R> p) {
   }
   const R NN = R(N) * R(N);
 
-  // Phase skew (M_ADAM launches with p.skew_split > 0): the warps of the CTA form two groups that run half a
-  // step apart, so the latency-bound parameter phase of one group overlaps the FMA-bound sweeps of the other.
-  // Half steps are separated by CTA-wide barriers (group B starts with one extra, group A ends with one extra);
-  // inside a sweep every group keeps its own per-layer barrier.
-  const bool skew = p.skew_split > 0;
-  const bool grp_b = skew && tid >= p.skew_split;
   LayerBar lb;
-  lb.id = skew ? (grp_b ? 2 : 1) : 0;
-  lb.cnt = skew ? (grp_b ? (int)blockDim.x - p.skew_split : p.skew_split) : (int)blockDim.x;
   lb.every = p.sync_every; lb.every_bwd = p.sync_every_bwd;
-  if (grp_b) cta_sync();
 
   R best = R(0), best_reg_v = R(0);
   bool improved_prev = false;
@@ -875,7 +858,6 @@ heis_kernel(const KParams<R> p) {
     }
     __syncwarp();
 
-    if (skew) cta_sync();
     // ---------------- forward sweep: Y = U V^dag ----------------
     V yr[N], yi[N];
 #pragma unroll
@@ -938,9 +920,7 @@ heis_kernel(const KParams<R> p) {
     // ---------------- Heisenberg sweep ----------------
     SWP::backward(p, lb, coef, stage, coef_cp, m, h);
     __syncwarp();
-    if (skew) cta_sync();
   }
-  if (skew && !grp_b) cta_sync();
 
   if (p.mode == M_ADAM && active) {
     // unpack the optimiser state into the caller's arrays
@@ -1048,19 +1028,6 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   p.sync_every = p.sync_every_bwd = HEIS_SYNC_EVERY_DEFAULT;
   if (const char* e = getenv("CPF_HEIS_SYNC_EVERY")) { int v = atoi(e); if (v >= 0) p.sync_every = p.sync_every_bwd = v; }
   if (const char* e = getenv("CPF_HEIS_SYNC_BWD")) { int v = atoi(e); if (v >= 0) p.sync_every_bwd = v; }
-  // phase skew: env CPF_HEIS_SKEW = percentage of the CTA's warps in group A (0 = off)
-  p.skew_split = 0;
-  {
-    int pct = HEIS_SKEW_DEFAULT;
-    if (const char* e = getenv("CPF_HEIS_SKEW")) { int v = atoi(e); if (v >= 0 && v < 100) pct = v; }
-    const int warps = g.block / 32;
-    if (p.mode == M_ADAM && pct > 0 && warps >= 2) {
-      int wa = (warps * pct + 50) / 100;
-      if (wa < 1) wa = 1;
-      if (wa > warps - 1) wa = warps - 1;
-      p.skew_split = wa * 32;
-    }
-  }
   if (g.smem > 227 * 1024) {
     err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
     return CPF_ERR_UNSUPPORTED;

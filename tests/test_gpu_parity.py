@@ -468,6 +468,20 @@ def test_heis_launch_geometry_edge_cases():
             assert torch.equal(lo, lo_ref[:B]) and torch.equal(gr, gr_ref[:B]), (B, env)
             assert torch.equal(st.angles, st_ref.angles[:B]) and torch.equal(st.best_params, st_ref.best_params[:B])
             assert torch.equal(st.best_regloss, st_ref.best_regloss[:B])
+    # complex64, a batch that fills the SMs: the automatic geometry takes two co-resident CTAs of 8 warps per SM
+    # (heis_geometry); one CTA of 16 warps and four small ones must give the same bits
+    a32 = anz.program.initial_angles(5, 64 * n_sm)
+
+    def run32():
+        st = anz.program.adam_state(a32.clone())
+        anz.program.adam_run(st, Loss("hs", V), pen(), 0.1, 7)
+        return st
+    ref = run32()
+    for env in ({"CPF_HEIS_CTAS": "1"}, {"CPF_HEIS_CTAS": "2", "CPF_HEIS_WARPS": "8"}, {"CPF_HEIS_CTAS": "4", "CPF_HEIS_WARPS": "3"},
+                {"CPF_HEIS_SYNC_EVERY": "1"}, {"CPF_HEIS_SYNC_EVERY": "0"}):
+        st = _with_env(env, run32)
+        assert torch.equal(st.angles, ref.angles) and torch.equal(st.best_regloss, ref.best_regloss), env
+        assert torch.equal(st.best_params, ref.best_params) and torch.equal(st.m, ref.m) and torch.equal(st.v, ref.v), env
 
 
 @pytest.mark.parametrize("n,layer,K", [(6, chain_layer(6), 9), (6, connected_layer(6), 17), (7, chain_layer(7), 8)])
