@@ -2,7 +2,7 @@
 # ncu full capture of heis_kernel on a short C3 run with full residency (57 samples per SM), then GPU tests + bench
 mkdir -p gpurun_out
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:^heis_kernel -c 1 -f -o gpurun_out/prof_heis \
-  python tools/prof_c3.py 9176 40 > gpurun_out/ncu_full.log 2>&1
+  python tools/prof_c3.py 9472 40 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python bench.py --no-cpu-baseline --no-static > gpurun_out/bench_quick.json; python -c "

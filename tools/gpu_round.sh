@@ -11,9 +11,9 @@ timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tai
 # launch list of the bench command (short run: same launches, fewer Adam iterations and samples)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 1 --iters 100 --no-cpu-baseline --no-static > gpurun_out/bench_under_ncu.log 2>&1
-# full capture of the engine kernel on a short C3 run (62 resident samples per SM like the bench launch)
+# full capture of the engine kernel on a short C3 run (2 CTAs x 32 resident samples per SM like the bench launch)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:^heis_kernel -c 1 -f -o gpurun_out/prof_heis \
-  python tools/prof_c3.py 9176 40 > gpurun_out/ncu_full.log 2>&1
+  python tools/prof_c3.py 9472 40 > gpurun_out/ncu_full.log 2>&1
 tail -1 gpurun_out/ncu_full.log
 # DRAM traffic of one bench launch (B = 10^5, T = 2000)
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:^heis_kernel -c 1 --csv \
