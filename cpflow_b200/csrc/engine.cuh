@@ -62,7 +62,7 @@ struct KParams {
   R* aux;           // heis_kernel: [B][n_su2][4] half-angle cos/sin of the 2nd and 3rd fused rotations
   int coef_stride;  // R words per sample in shared memory
   int spb;          // heis_kernel: sample slots used per CTA
-  int sync_every, sync_every_bwd;   // heis_kernel: CTA barrier at every n-th layer of the forward / backward sweep
+  int sync_sweeps;  // heis_kernel: CTA barrier at the start of the forward (bit 0) / backward (bit 1) sweep
   int colmode;      // engine_kernel<SINGLE>, M_UNITARY: virtual sample b = (sample b / N, column b % N)
   int axp_surface, axp_block;   // heis_kernel: packed rotation axes shared by the surface / block gates
   int last_slot[8];             // heis_kernel: slot of the last fused gate on each qubit

@@ -40,7 +40,6 @@ constexpr int HEIS_SU2_WORDS = 8;
 // (cos theta, -+sin theta, cos zeta | 1, sin zeta | 0): row 0 for lanes that hold (I, Z) of the gate's qubit, row 1
 // for lanes that hold (X, Y).  A lane picks its row by address: no selects.
 constexpr int HEIS_STAGE_WORDS = 8;
-constexpr int HEIS_SYNC_EVERY_DEFAULT = 1 << 20;   // layers between CTA barriers inside a sweep (first layer always)
 constexpr int HEIS_CP_WORDS = 3;     // cos(a/2) >= 0, sin(a/2), -tan(a/4); word 0 <- dL/da after the backward sweep
 
 inline int heis_coef_stride(int n_su2, int n_cp, int n_stage) {
@@ -72,11 +71,10 @@ struct HCfg {
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
 };
 
-// CTA barriers inside the sweeps keep the warps of a CTA on the same instruction-cache lines: one at every
-// `every`-th layer of the forward / backward sweep, counted from the first (0 = never).
+// A CTA barrier at the start of each sweep keeps the warps of a CTA on the same instruction-cache lines (a barrier
+// per layer, the first design, cost 7 %; none at all 20 %).  fwd / bwd: barrier before the forward / backward sweep.
 struct LayerBar {
-  int every, every_bwd;
-  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  bool fwd, bwd;
 };
 
 // Store to shared memory under a predicate, without a branch (the compiler turns `if (lane == k) s[i] = v`
@@ -165,10 +163,8 @@ struct HeisSweep {
     const int K = p.n_cp;
     const R* cs = coef + SW * NQ;
 #pragma unroll 1
-    int li = 0;
+    if (lb.fwd) __syncthreads();
     for (int k0 = 0; k0 < K; k0 += NBL) {
-      if (li == 0 && lb.every > 0) lb.sync();   // keep the warps of the group on the same instruction-cache lines
-      li = li + 1 == lb.every ? 0 : li + 1;
       blocks_fwd<0>(k0, K, cs, yr, yi);
       cs += 2 * SW * NBL;
     }
@@ -405,12 +401,10 @@ struct HeisSweep {
   static __device__ __forceinline__ void backward(const KParams<R>& p, const LayerBar lb, R* coef, R* stage, R* cph0,
                                                   int m, V (&h)[N]) {
     const int K = p.n_cp;
+    if (lb.bwd) __syncthreads();
     tail_bwd<0>(p, coef, m, h);
-    int li = 0;
 #pragma unroll 1
     for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL) {
-      if (li == 0 && lb.every_bwd > 0) lb.sync();
-      li = li + 1 == lb.every_bwd ? 0 : li + 1;
       stage_layer(k0, K, coef, cph0, stage, m);
       __syncwarp();
       blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
@@ -764,7 +758,7 @@ heis_kernel(const KParams<R> p) {
   const R NN = R(N) * R(N);
 
   LayerBar lb;
-  lb.every = p.sync_every; lb.every_bwd = p.sync_every_bwd;
+  lb.fwd = (p.sync_sweeps & 1) != 0; lb.bwd = (p.sync_sweeps & 2) != 0;
 
   R best = R(0), best_reg_v = R(0);
   bool improved_prev = false;
@@ -1023,11 +1017,9 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes + heis_meta_bytes(p.n_su2, p.n_cp),
                                        (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT, regs);
   p.spb = g.spb;
-  // CTA barriers inside the sweeps (they keep the warps on the same instruction-cache lines): one at the start
-  // of each sweep is enough to stop the warps drifting apart; a barrier per layer costs 7 % (B200, C3)
-  p.sync_every = p.sync_every_bwd = HEIS_SYNC_EVERY_DEFAULT;
-  if (const char* e = getenv("CPF_HEIS_SYNC_EVERY")) { int v = atoi(e); if (v >= 0) p.sync_every = p.sync_every_bwd = v; }
-  if (const char* e = getenv("CPF_HEIS_SYNC_BWD")) { int v = atoi(e); if (v >= 0) p.sync_every_bwd = v; }
+  // CTA barrier at the start of the forward (bit 0) / backward (bit 1) sweep; env CPF_HEIS_SYNC overrides (tests)
+  p.sync_sweeps = 3;
+  if (const char* e = getenv("CPF_HEIS_SYNC")) { int v = atoi(e); if (v >= 0 && v <= 3) p.sync_sweeps = v; }
   if (g.smem > 227 * 1024) {
     err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
     return CPF_ERR_UNSUPPORTED;

@@ -478,7 +478,7 @@ def test_heis_launch_geometry_edge_cases():
         return st
     ref = run32()
     for env in ({"CPF_HEIS_CTAS": "1"}, {"CPF_HEIS_CTAS": "2", "CPF_HEIS_WARPS": "8"}, {"CPF_HEIS_CTAS": "4", "CPF_HEIS_WARPS": "3"},
-                {"CPF_HEIS_SYNC_EVERY": "1"}, {"CPF_HEIS_SYNC_EVERY": "0"}):
+                {"CPF_HEIS_SYNC": "0"}, {"CPF_HEIS_SYNC": "1"}):
         st = _with_env(env, run32)
         assert torch.equal(st.angles, ref.angles) and torch.equal(st.best_regloss, ref.best_regloss), env
         assert torch.equal(st.best_params, ref.best_params) and torch.equal(st.m, ref.m) and torch.equal(st.v, ref.v), env
