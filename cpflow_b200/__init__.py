@@ -8,3 +8,4 @@ from .engine import Loss, Penalty, Program  # noqa: F401
 from .ansatz import Ansatz  # noqa: F401
 from .main import (AdaptiveOptions, BasicOptions, Decomposition, RegularizationOptions, Results,  # noqa: F401
                    StaticOptions, Synthesize)
+from .legacy import load_reference_results  # noqa: F401,E402
