@@ -159,6 +159,8 @@ int stage_target(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KPara
   return CPF_OK;
 }
 
+struct cpf_loss_spec_kind_only { int32_t kind; };
+
 // Per-call scratch (packed optimiser state, staged targets) comes from the device's default stream-ordered pool.
 // Its release threshold defaults to 0: freed blocks go back to the driver at the next synchronisation and the
 // next call pays for mapping hundreds of megabytes again.  Keep them in the pool (once per device and process).
@@ -443,6 +445,29 @@ __global__ void initial_angles_kernel(const cpf::CpMeta* cp, int n_cp, int P, ui
 
 }  // namespace
 
+template <typename R>
+static int launch_plan_t(const cpf::Program* prog, const cpf_loss_spec_kind_only& lk, int64_t batch, int n_sm, int regs,
+                         cpf_launch_info* out) {
+  cpf_loss_spec ls{};
+  ls.kind = lk.kind;
+  const bool heis = use_heis<R>(prog, &ls) && (unsigned long long)batch * (unsigned long long)prog->n_params < (1ull << 32);
+  out->engine = heis ? 1 : 0;
+  if (!heis) return CPF_OK;
+  const int n = prog->n_qubits, N = 1 << n, cpt = cpf::heis_cpt<R>(n), tps = N / cpt;
+  const int maxt = 2 * N * cpt * (int)(sizeof(R) / 4) <= 64 ? 512 : 256;          // HCfg::MAXT
+  const int n_su2 = (int)prog->su2.size(), n_cp = (int)prog->cp.size();
+  const int n_stage = 2 * prog->period > n ? 2 * prog->period : n;                // HeisSweep::NSTAGE
+  const int stride = cpf::heis_coef_stride(n_su2, n_cp, n_stage);
+  const size_t target = (((size_t)cpf::heis_target_words<R>(n, cpt) * sizeof(R)) + 15) & ~(size_t)15;
+  const cpf::HeisGeometry g = cpf::heis_geometry(batch, target + cpf::heis_meta_bytes(n_su2, n_cp),
+                                                 (size_t)stride * sizeof(R), tps, maxt, regs > 0 ? regs : 128,
+                                                 n_sm > 0 ? n_sm : 148);
+  out->ctas_per_sm = g.ctas; out->block_threads = g.block; out->samples_per_cta = g.spb; out->grid = g.grid;
+  out->smem_bytes = (int64_t)g.smem; out->threads_per_sample = tps; out->max_block_threads = maxt;
+  out->words_per_sample = stride;
+  return CPF_OK;
+}
+
 extern "C" {
 
 int cpf_version(void) { return CPF_VERSION; }
@@ -633,6 +658,17 @@ int cpf_eval_cost(const cpf_program* prog, int32_t loss_kind, int32_t dtype, dou
   if (flops) *flops = C * N * (16.0 * p->n_rot + 4.0 * p->n_phase + 8.0);
   if (bytes) *bytes = 6.0 * p->n_params * rs + 2.0 * rs;
   return CPF_OK;
+}
+
+int cpf_launch_plan(const cpf_program* prog, int32_t loss_kind, int32_t dtype, int64_t batch, int32_t n_sm,
+                    int32_t regs_per_thread, cpf_launch_info* out) {
+  if (!prog || !out) return fail(CPF_ERR_INVALID, "NULL argument");
+  if (batch < 0) return fail(CPF_ERR_INVALID, "negative batch");
+  std::memset(out, 0, sizeof(*out));
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  const cpf_loss_spec_kind_only lk{loss_kind};
+  return dtype == CPF_F64 ? launch_plan_t<double>(p, lk, batch, n_sm, regs_per_thread, out)
+                          : launch_plan_t<float>(p, lk, batch, n_sm, regs_per_thread, out);
 }
 
 }  // extern "C"

@@ -965,10 +965,14 @@ inline long long heis_cap(int ctas, size_t fixed_bytes, size_t per_sample, int t
   if (cap > cap_thr) cap = cap_thr;
   return cap < 1 ? 1 : cap;
 }
-inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sample, int tps, int maxt, int regs) {
-  int dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sample, int tps, int maxt, int regs,
+                                  int n_sm = 0) {
+  if (n_sm <= 0) {          // the current device (cpf_launch_plan passes a number to plan without one)
+    int dev = 0;
+    n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
   int ctas = 0, warps_env = 0;
   if (const char* e = getenv("CPF_HEIS_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctas = v; }
   if (const char* e = getenv("CPF_HEIS_WARPS")) { int v = atoi(e); if (v >= 1) warps_env = v; }
@@ -976,7 +980,8 @@ inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sa
   auto spread = [&](int nc, long long& spb_out) {
     const long long cap = heis_cap(nc, fixed_bytes, per_sample, tps, maxt, regs, warps_env);
     const long long slots = slots1 * nc;
-    const long long rounds = (B + slots * cap - 1) / (slots * cap);
+    long long rounds = (B + slots * cap - 1) / (slots * cap);
+    if (rounds < 1) rounds = 1;               // empty batch
     long long spb = (B + slots * rounds - 1) / (slots * rounds);
     if (spb > cap) spb = cap;
     if (spb < 1) spb = 1;

@@ -66,6 +66,13 @@ class Program:
         L.check(L.load().cpf_eval_cost(self._h, int(loss_kind), _DT[dtype], C.byref(f), C.byref(b)))
         return f.value, b.value
 
+    def launch_plan(self, batch, loss_kind=L.LOSS_HS, dtype=torch.float32, n_sm=0, regs_per_thread=0):
+        """The launch geometry the engine would use for `batch` samples (cpf_launch_plan; needs no device)."""
+        info = L.CpfLaunchInfo()
+        L.check(L.load().cpf_launch_plan(self._h, int(loss_kind), _DT[dtype], int(batch), int(n_sm),
+                                         int(regs_per_thread), C.byref(info)))
+        return {name: getattr(info, name) for name, _ in info._fields_ if name != "reserved"}
+
     # ---- forward / gradients -------------------------------------------------------------
     def unitary(self, angles):
         _need_cuda(angles)

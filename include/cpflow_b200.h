@@ -209,6 +209,25 @@ int cpf_initial_angles(const cpf_program* prog, int32_t dtype, uint64_t seed,
 int cpf_eval_cost(const cpf_program* prog, int32_t loss_kind, int32_t dtype, double* flops,
                   double* bytes);
 
+/* Diagnostics: the launch geometry cpf_adam_run / cpf_loss_grad would use for `batch` samples (no reference
+ * counterpart; it makes the geometry rules testable without a device).  engine: 1 = Heisenberg-picture kernel
+ * (HS loss on a layered template), 0 = state-adjoint kernel (the remaining fields are 0).  n_sm / regs_per_thread:
+ * 0 = 148 SMs / 128 registers (nothing is queried from a device). */
+typedef struct cpf_launch_info {
+  int32_t engine;
+  int32_t ctas_per_sm;        /* co-resident CTAs per SM the geometry was planned for */
+  int32_t block_threads;      /* multiple of 32 */
+  int32_t samples_per_cta;
+  int32_t threads_per_sample;
+  int32_t max_block_threads;
+  int32_t words_per_sample;   /* shared-memory words (of the real type) per sample */
+  int32_t reserved;
+  int64_t grid;
+  int64_t smem_bytes;         /* dynamic shared memory per CTA */
+} cpf_launch_info;
+int cpf_launch_plan(const cpf_program* prog, int32_t loss_kind, int32_t dtype, int64_t batch, int32_t n_sm,
+                    int32_t regs_per_thread, cpf_launch_info* out);
+
 #ifdef __cplusplus
 }
 #endif

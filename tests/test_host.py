@@ -144,3 +144,43 @@ def test_product_path_has_no_cpu_fallback():
     for m in pkgutil.iter_modules(cpflow_b200.__path__):
         src = open(os.path.join(cpflow_b200.__path__[0], m.name + ".py")).read() if not m.ispkg else ""
         assert "oracle" not in src.replace("oracle restates", ""), m.name
+
+
+def test_launch_plan_geometry_rules(lib):
+    """cpf_launch_plan (heis_geometry, csrc/heis_impl.cuh) without a device: every plan covers the batch, fits the
+    thread, register and shared-memory limits of an SM, and the documented choices hold (two co-resident CTAs only
+    when each keeps 8 warps and the SM as many samples as with one)."""
+    import torch
+    from cpflow_b200.engine import Program  # noqa: F401
+    cases = [(2, [[0, 1]], 3), (3, T.chain_layer(3), 12), (3, T.connected_layer(3), 7), (4, T.chain_layer(4), 40),
+             (4, [[0, 1], [0, 2], [0, 3]], 40), (4, T.connected_layer(4), 61), (5, T.chain_layer(5), 60),
+             (5, T.connected_layer(5), 60)]
+    for n, layer, K in cases:
+        anz = A.Ansatz(n, "cp", T.fill_layers(layer, K))
+        n_su2, n_cp, nbl = n + 2 * K, K, len(layer)
+        for dt, rs in ((torch.float32, 4), (torch.float64, 8)):
+            if dt == torch.float64 and n == 5:
+                assert anz.program.launch_plan(1000, dtype=dt)["engine"] == 0       # 5-qubit c128: state-adjoint kernel
+                continue
+            for B in (0, 1, 7, 147, 148, 149, 1000, 12500, 100000, 1000003):
+                for regs in (96, 118, 128):
+                    p = anz.program.launch_plan(B, dtype=dt, n_sm=148, regs_per_thread=regs)
+                    assert p["engine"] == 1
+                    tps, spc, blk, ctas = p["threads_per_sample"], p["samples_per_cta"], p["block_threads"], p["ctas_per_sm"]
+                    words = 8 * n_su2 + 3 * n_cp + 8 * max(2 * nbl, n)
+                    assert p["words_per_sample"] >= words and p["words_per_sample"] - words < 8
+                    assert (p["words_per_sample"] // 4) % 2 == 1                      # odd number of 16-byte groups
+                    assert blk % 32 == 0 and 32 <= blk <= p["max_block_threads"] and spc * tps <= blk < spc * tps + 32
+                    assert p["grid"] * spc >= B and (p["grid"] - 1) * spc < max(B, 1)
+                    assert ctas in (1, 2) and ctas * (p["smem_bytes"] + 1024) <= 227 * 1024
+                    regs_warp = (regs * 32 + 255) // 256 * 256
+                    assert ctas * (blk // 32) * regs_warp <= 65536
+                    if ctas == 2:
+                        assert blk >= 256
+                    assert p["smem_bytes"] >= spc * p["words_per_sample"] * rs
+    c3 = A.Ansatz(4, "cp", T.fill_layers(T.chain_layer(4), 40)).program
+    p = c3.launch_plan(100000, n_sm=148, regs_per_thread=118)
+    assert (p["ctas_per_sm"], p["block_threads"], p["samples_per_cta"]) == (2, 256, 31)      # the bench launch
+    p = c3.launch_plan(12500, n_sm=148, regs_per_thread=118)
+    assert (p["ctas_per_sm"], p["block_threads"], p["samples_per_cta"]) == (1, 352, 43)
+    assert c3.launch_plan(100, loss_kind=L.LOSS_STATE)["engine"] == 0
