@@ -184,3 +184,25 @@ def test_launch_plan_geometry_rules(lib):
     p = c3.launch_plan(12500, n_sm=148, regs_per_thread=118)
     assert (p["ctas_per_sm"], p["block_threads"], p["samples_per_cta"]) == (1, 352, 43)
     assert c3.launch_plan(100, loss_kind=L.LOSS_STATE)["engine"] == 0
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the CUDA arm): one JSON line on stdout with
+    the contract's keys; ranks other than 0 print nothing."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-samples", "8", "--cpu-iters", "2"]
+    env = dict(os.environ, RANK="0")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["metric"].startswith("loss+grad evals/sec") and d["config"]["workload"].startswith("C3")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
+    assert out.returncode == 0 and out.stdout.strip() == ""
