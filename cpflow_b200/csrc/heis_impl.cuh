@@ -15,14 +15,18 @@
 //             h[x, z] = Re(i^{|x&z|} s W[x,z]),  W[x,z] = sum_r (-1)^{|z&r|} Y[r, r^x]
 //             are N^2 REAL numbers: one xor-shuffle all-to-all gathers the x-diagonals (lane = x >> PB)
 //             and a register-local Walsh-Hadamard transform over r produces W.
-//   backward  H_{k-1} = G_k^dag H_k G_k acts on h by real linear maps: a fused one-qubit gate rotates
-//             (h_X, h_Y, h_Z) of its qubit with the transpose of its SO(3) matrix (packed over the register x bit:
-//             4 FFMA2 + 1 SHFL per pair when the qubit's x bit is a lane bit); CP(a) ~ Rz Rz exp(i a/4 ZZ): the Rz
-//             halves are folded into the SO(3) matrices, the ZZ part is a pair rotation by a/2.
+//   backward  H_{k-1} = G_k^dag H_k G_k acts on h by real linear maps.  Every fused gate is used as
+//             Rz(phi_out + pi/2) Rx(theta) Rz(phi_in - pi/2): Rx mixes (h_Y, h_Z) (2 FFMA2 + 1 SHFL per packed pair
+//             when the qubit's x bit is a lane bit, the exchanged value is the raw register), Rz mixes
+//             (h_X, h_Y) inside a lane (4 FFMA2); the Rz factors of consecutive gates on a qubit, the Rz halves of
+//             CP(a) ~ Rz Rz exp(i a/4 ZZ) and the pending phases commute and are undone as ONE rotation per gate;
+//             the ZZ part is a pair rotation by a/2 in lifting form (three shears).
 //             Every gradient entry is ONE coefficient of h (X: h[b,0], Y: h[b,b], Z: h[0,b]; CP:
 //             -(h[0,0]-h[0,b1]-h[0,b2]+h[0,b1|b2])/2): no reductions.
 //
-// Per sample and eval for C3 (n = 4, K = 40): ~7.0 k warp instructions (x 1/4 warp) instead of ~22 k.
+// Shared memory per sample: 8 words per fused gate + 3 per entangler + a staging area for the coefficients of
+// ONE layer of the backward sweep (produced just in time from the forward data), see HEIS_SU2_WORDS below.
+// Per sample and eval for C3 (n = 4, K = 40): ~5.6 k warp instructions (x 1/4 warp) instead of ~22 k.
 #pragma once
 #include "engine_impl.cuh"
 
@@ -287,7 +291,7 @@ struct HeisSweep {
   static __device__ __forceinline__ bool xlane(int m) { return ((m >> (B - PB)) & 1) != 0; }
 
   // Entangler of a block on amplitude bits (B1, B2).  CP(a) ~ Rz_1(a/2) Rz_2(a/2) exp(i (a/4) Z1 Z2): the two Rz
-  // are folded into the SO(3) matrices of the block's fused gates (heis_su2_to_so3), what remains rotates,
+  // join the merged Rz rotation of the block's fused gates (stage_layer: zeta), what remains rotates,
   // for coefficients whose x bits on the two qubits differ, the pairs (e00, e11) and (e01, e10) of every
   // (z1, z2) quad by a/2.  cf: cos(a/2), sin(a/2); word 0 receives dL/da = -(h_II - h_ZI - h_IZ + h_ZZ)/2
   // (Z-type coefficients: they do not see the Rz shuffle).
@@ -590,7 +594,7 @@ __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const U
   return in;
 }
 
-// Fused one-qubit gate: finish the step (chain rule through the fusion, Adam), then the new (alpha, beta).
+// Fused one-qubit gate: finish the step (chain rule through the fusion, Adam), then the new ZYZ data of the gate.
 // AX* >= 0: compile-time rotation axes (the selects fold away); AX0 == -2: axes from the gate metadata.
 template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, const Su2Meta* md,
