@@ -184,6 +184,8 @@ static void keep_pool_memory() {
 template <typename R>
 bool use_heis(const cpf::Program* prog, const cpf_loss_spec* loss) {
   if (loss->kind != CPF_LOSS_HS || !prog->layered) return false;
+  // the kernel's shared-memory metadata holds parameter and slot indices in 16 bits (heis_impl.cuh: HSu2, HCp)
+  if (prog->n_params > 32767 || prog->su2.size() > 32767) return false;
   const char* e = getenv("CPF_ENGINE");
   if (e && std::strcmp(e, "adjoint") == 0) return false;
   const char* nl = getenv("CPF_NO_LAYERED");
