@@ -177,8 +177,19 @@ class Results:
 
     @staticmethod
     def load(path):
-        with open(path, 'rb') as f:
-            return _pickler.load(f)
+        """main.py:458-461.  Files written by the reference itself (they name cpflow / qiskit / hyperopt / jax
+        classes that are not installed here) are read through `legacy.load_reference_results`."""
+        try:
+            with open(path, 'rb') as f:
+                res = _pickler.load(f)
+            if isinstance(res, Results):
+                return res
+        except FileNotFoundError:
+            raise
+        except Exception:      # ModuleNotFoundError / AttributeError of a foreign class path, dill helpers, ...
+            pass
+        from .legacy import load_reference_results
+        return load_reference_results(path)
 
     def best_hyperparameters(self):
         """Pairs [num_cp_gates, r] ordered by increasing score (main.py:471-477)."""

@@ -124,3 +124,18 @@ def test_reference_files_against_golden_fixtures():
             assert d.cz_count == sum(g.name == "cz" for g in d.circuit.data)
             n_circ += 1
     assert n_circ > 30 and n_tight >= 0.9 * n_circ
+
+
+def test_results_load_falls_back_to_the_reference_format(fake_reference_file, tmp_path):
+    """Results.load (main.py:458-461) reads this package's own files and the reference's."""
+    from cpflow_b200.main import Results, Trials
+    path, u, _ = fake_reference_file
+    res = Results.load(path)
+    assert isinstance(res, Results) and res.label == "fake" and len(res.decompositions) == 1
+    own = Results(None, [[0, 1]], label="own", trials=Trials(), save_to=str(tmp_path / "own_results"))
+    own.trials.results.append({"loss": 1.0, "num_cp_gates": 3, "r": 0.1})
+    own.save()
+    back = Results.load(own.save_to)
+    assert isinstance(back, Results) and back.label == "own" and back.best_hyperparameters() == [[3, 0.1]]
+    with pytest.raises(FileNotFoundError):
+        Results.load(str(tmp_path / "missing"))
