@@ -206,3 +206,35 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_built_kernels_fit_the_planned_occupancy():
+    """Resource usage of the built sm_100a kernels (cuobjdump -res-usage on the in-tree library): the Heisenberg
+    kernels of the complex64 templates up to 4 qubits must stay within 128 registers (two co-resident CTAs of 8
+    warps, heis_geometry) without a spill frame beyond the sincos fallback's 32 bytes; every engine kernel targets
+    sm_100a."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", L.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    assert "sm_100a" in out
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.match(r"\s*REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+    heis32 = {k: v for k, v in usage.items() if "heis_kernelIfLi" in k}
+    assert len(heis32) >= 8
+    for k, (regs, stack) in heis32.items():
+        assert regs <= 128, (k, regs)
+        if "heis_kernelIfLi5" not in k:                       # 5 qubits: one warp per sample, small spill accepted
+            assert stack <= 32, (k, stack)
+    c3 = [v for k, v in heis32.items() if "HeisSweepIfLi4ELi2ELi3ELy528ELy801" in k]
+    assert c3 and c3[0][0] <= 120        # the bench kernel: 2 CTAs x 256 threads x regs <= 64 K with room
