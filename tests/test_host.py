@@ -208,7 +208,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_built_kernels_fit_the_planned_occupancy():
+def test_built_kernels_fit_the_planned_occupancy(lib):
     """Resource usage of the built sm_100a kernels (cuobjdump -res-usage on the in-tree library): the Heisenberg
     kernels of the complex64 templates up to 4 qubits must stay within 128 registers (two co-resident CTAs of 8
     warps, heis_geometry) without a spill frame beyond the sincos fallback's 32 bytes; every engine kernel targets
