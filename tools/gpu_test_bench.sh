@@ -1,4 +1,5 @@
 #!/bin/bash
+# GPU tests (default engine and the gate-list interpreter) and a quick bench line: one gpurun call.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12
 CPF_NO_LAYERED=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
