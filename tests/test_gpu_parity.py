@@ -16,57 +16,52 @@ from cpflow_b200 import _lib as L
 from cpflow_b200.ansatz import Ansatz
 from cpflow_b200.engine import Loss, Penalty, Program
 from cpflow_b200.gates import u_toff3, u_toff4
-from cpflow_b200.penalty import RegularizationOptions, make_regularization_function
 from cpflow_b200.topology import chain_layer, connected_layer, fill_layers
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-PF = make_regularization_function(RegularizationOptions)
-TOL = {torch.float64: 1e-12, torch.float32: 1e-5}
-CONFIGS = [(3, chain_layer(3), 5, "xyz"), (4, [[0, 1], [0, 2], [0, 3]], 10, "xyz"), (2, [[0, 1]], 3, "xz"),
-           (5, connected_layer(5), 12, "xyz"), (4, [[3, 1], [2, 0]], 7, "zyx"), (4, chain_layer(4), 40, "xyz"),
-           (3, connected_layer(3), 7, "xyz"), (5, chain_layer(5), 9, "xz")]
-
-
-def pen(r=0.01):
-    return Penalty("piecewise", r, PF.segments, PF.period)
-
-
-def rel(a, b):
-    return float(np.abs(a - b).max() / max(1e-30, np.abs(b).max()))
-
-
-def setup(n, layer, K, rg):
-    anz = Ansatz(n, "cp", fill_layers(layer, K), rg)
-    oanz = O.cp_ansatz(layer, K, rg)
-    return anz, oanz, O.ansatz_program(oanz)
+from parity_lib import CONFIGS, KITE4, PF, SQUARE4, STAR4, TOL, measure_adam_loop, measure_loss_grad, pen, rel, setup  # noqa: E402
 
 
 @pytest.mark.parametrize("n,layer,K,rg", CONFIGS)
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 def test_unitary_loss_grad_parity(n, layer, K, rg, dt):
-    anz, oanz, ops = setup(n, layer, K, rg)
-    N, B = 2 ** n, 37  # ragged: not a multiple of the samples-per-block
-    a64 = np.random.default_rng(n * 100 + K).uniform(0, 2 * np.pi, (B, anz.num_angles))
-    a = torch.tensor(a64, dtype=dt, device=DEV)
-    a_o = torch.tensor(a.cpu().numpy().astype(np.float64))  # the oracle sees the rounded inputs
-    u = anz.program.unitary(a).cpu().numpy()
-    uo = O.program_unitary_batched(n, ops, a_o).numpy()
-    assert np.abs(u - uo).max() < (1e-13 if dt == torch.float64 else 5e-6)
-    V = unitary_group.rvs(N, random_state=1)
-    for kind, tgt in [("hs", V), ("relphase", V), ("state", V[:, 0].copy())]:
-        lo, rg_, gr = anz.program.loss_grad(a, Loss(kind, tgt), pen())
-        ol, orr, og = O.loss_and_grad_batched(n, ops, a_o, kind, torch.tensor(tgt), oanz.cp_mask, 0.01,
-                                              O.make_regularization_function())
-        tol = TOL[dt]
-        assert rel(lo.cpu().numpy(), ol.numpy()) < tol * (1 if dt == torch.float64 else 2), kind
-        assert rel(rg_.cpu().numpy(), orr.numpy()) < tol * (1 if dt == torch.float64 else 2), kind
-        g, og = gr.cpu().numpy().astype(np.float64), og.numpy()
-        gn = np.linalg.norm(g - og, axis=1) / np.linalg.norm(og, axis=1)
-        assert gn.max() < tol * (1 if dt == torch.float64 else 2), (kind, gn.max())
-        # loss-only call gives the same loss bits
-        lo2, _, none = anz.program.loss_grad(a, Loss(kind, tgt), pen(), want_grad=False)
-        assert none is None and torch.equal(lo, lo2)
+    """Loss, penalty and gradient of all three losses on a ragged batch of generic angles against the oracle, at
+    the contract's tolerance: 1e-5 (complex64) / 1e-12 (complex128).  tools/parity_report.py prints the measured
+    maxima of the same function (profiles/parity_r2.txt)."""
+    m = measure_loss_grad(n, layer, K, rg, dt)
+    tol = TOL[dt]
+    assert m["unitary"] < (1e-13 if dt == torch.float64 else 5e-6)
+    for kind in ("hs", "relphase", "state"):
+        e = m[kind]
+        assert e["loss"] < tol and e["reg"] < tol and e["grad"] < tol, (kind, e)
+        assert e["loss_only_same_bits"], kind
+
+
+@pytest.mark.parametrize("layer_name,layer", [("chain", chain_layer(4)), ("star", STAR4)])
+@pytest.mark.parametrize("freeze", [False, True])
+def test_adam_loop_parity_c3_shape(layer_name, layer, freeze):
+    """The kernel the bench times (4 qubits, K = 40, chain and star; HeisSweep) against the oracle's loop over
+    T = 150 Adam iterations of 32 samples in complex128: initial / best regloss, best reg, best parameters at 1e-9,
+    and the verification variant (projected CP angles frozen, no penalty; cp_utils.py:205-247).  The oracle's
+    outputs are the committed fixture tests/golden/adam_c3.npz (make_adam_c3.py; the CPU suite re-derives it)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adam_c3.npz"))
+    expect = {k: z[f"{layer_name}_{int(freeze)}_{k}"] for k in ("init_regloss", "best_regloss", "best_reg", "best_params")}
+    m = measure_adam_loop(4, layer, 40, u_toff4, B=32, T=150, freeze=freeze, expect=expect)
+    assert m["engine"] == 1, "C3 must run on the Heisenberg kernel"
+    assert m["init_regloss"] < 1e-12 and m["best_regloss"] < 1e-9 and m["best_reg"] < 1e-9, m
+    assert m["best_params"] < 1e-7, m
+    if freeze:
+        assert m["frozen_moved"] == 0.0
+
+
+def test_adam_loop_parity_c3_shape_f32():
+    """Same kernel in complex64 (the PLAIN instantiation of the bench) over a short horizon: trajectories are
+    chaotic in float32, so the loop is pinned over 10 iterations."""
+    m = measure_adam_loop(4, chain_layer(4), 40, u_toff4, B=32, T=10, dt=torch.float32)
+    assert m["engine"] == 1
+    assert m["init_regloss"] < 2e-6 and m["best_regloss"] < 2e-4 and m["best_reg"] < 2e-4, m
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
@@ -328,7 +323,7 @@ def test_full_size_properties_c3(layer_name):
     lo64, rg64, gr64 = prog.loss_grad(a[:512].double(), Loss("hs", u_toff4), pen(0.001476))
     assert rel(lo[:512].cpu().numpy(), lo64.cpu().numpy()) < 1e-5
     gn = (gr[:512].double() - gr64).norm(dim=1) / gr64.norm(dim=1)
-    assert float(gn.max()) < 2e-5
+    assert float(gn.max()) < 1e-5
     perm = torch.randperm(B, device=DEV)
     lo_p, _, gr_p = prog.loss_grad(a[perm].contiguous(), Loss("hs", u_toff4), pen(0.001476))
     assert torch.equal(lo_p, lo[perm]) and torch.equal(gr_p, gr[perm])
@@ -352,7 +347,7 @@ def _assert_same_run(x, y, dt, ctx=None):
     quantities agree to rounding.  Adam trajectories amplify gradient rounding by lr / (|g| + eps) wherever a
     gradient component is tiny (first steps: update = lr g / (|g| + eps)), so angles are compared at
     1e-10 in f64 and only loosely in f32 (one Adam step is pinned exactly by test_first_adam_step_closed_form)."""
-    tol = 1e-12 if dt == torch.float64 else 2e-5
+    tol = 1e-12 if dt == torch.float64 else 1e-5
     for a, b in zip(x[:2], y[:2]):
         assert float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max())), ctx
     assert float((x[2] - y[2]).abs().max()) <= (1e-10 if dt == torch.float64 else 2e-4), ctx
@@ -501,7 +496,7 @@ def test_six_seven_qubit_state_preparation(n, layer, K, dt):
     lo, rg_, gr = anz.program.loss_grad(a, Loss("state", psi), pen())
     ol, orr, og = O.loss_and_grad_batched(n, ops, a_o, "state", torch.tensor(psi), oanz.cp_mask, 0.01,
                                           O.make_regularization_function())
-    tol = TOL[dt] * (1 if dt == torch.float64 else 2)
+    tol = TOL[dt]
     assert rel(lo.cpu().numpy(), ol.numpy()) < tol and rel(rg_.cpu().numpy(), orr.numpy()) < tol
     g, og = gr.cpu().numpy().astype(np.float64), og.numpy()
     assert (np.linalg.norm(g - og, axis=1) / np.linalg.norm(og, axis=1)).max() < tol

@@ -250,3 +250,17 @@ def test_projection_and_counting():
     out, frozen = O.project_cp_angles(a, mask)
     assert list(frozen) == [True, True, False, True, False, True]
     assert out[0] == 0 and out[1] == np.float32(math.pi) and out[2] == a[2] and out[3] == 0 and out[4] == a[4]
+
+
+def test_adam_c3_fixture_is_the_oracle():
+    """tests/golden/adam_c3.npz (the oracle's Adam loop on the bench's 4-qubit K = 40 shape, compared with the CUDA
+    kernel by tests/test_gpu_parity.py) re-derived here for its verification-variant star case: the stored arrays must
+    be what the oracle produces now from the same inputs (T = 150; 1e-12: BLAS reduction order may differ per host)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity_lib as P
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adam_c3.npz"))
+    res = P.oracle_adam_case(4, P.STAR4, 40, O.toffoli_target(4).numpy(), 32, 150, True)
+    for k, v in res.items():
+        assert np.abs(z[f"star_1_{k}"] - v).max() < 1e-12, k
