@@ -199,6 +199,24 @@ def cp_to_cz_circuit(circuit, cp_threshold=0.2):
     return out
 
 
+def cp_template_cz_count_depth(all_placements, cp_angles, num_qubits, cp_threshold=1e-6):
+    """CZ count and CZ depth of `cp_to_cz_circuit(template)` for a batch of CP-angle vectors [B,K] without building
+    the circuits: CP(a) contributes 0 / 1 / 2 CZ gates by the rule above (on the raw angle), and the two CZ of the
+    two-CZ form sit back to back on the same pair, so the depth is a per-qubit level scan over the blocks
+    (`Circuit.depth` restricted to CZ gates)."""
+    a = np.asarray(cp_angles, dtype=np.float64)
+    mult = np.where(np.abs(a) <= cp_threshold, 0, np.where(np.abs(a - math.pi) <= cp_threshold, 1, 2))
+    level = np.zeros((a.shape[0], num_qubits), dtype=np.int64)
+    for k, (q0, q1) in enumerate(all_placements):
+        m = mult[:, k]
+        lv = np.maximum(level[:, q0], level[:, q1]) + m
+        on = m > 0
+        level[on, q0] = lv[on]
+        level[on, q1] = lv[on]
+    depth = level.max(1) if num_qubits else np.zeros(a.shape[0], dtype=np.int64)
+    return mult.sum(1), depth
+
+
 def convert_to_ZXZ(circuit, drop_tol=1e-9):
     """exact_decompositions.py:176-190: merge every run of single-qubit gates into one SU(2) and
     re-express it as rz rx rz, dropping rotations whose angle is 0 mod 2 pi."""

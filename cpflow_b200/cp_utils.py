@@ -81,23 +81,7 @@ def convert_cp_to_cz(anz, angles, threshold=0.2):
     projected_cp_angles = proj[projected_indices]
     free_idx = [i for i in range(len(angles)) if not frozen[i]]
     free_angles = angles[free_idx]
-    prog, _ = anz.constrained(projected_cp_angles, projected_indices)
-
-    def full(free):
-        return insert_params(np.asarray(free), projected_cp_angles, projected_indices)
-
-    def circ_func(free):
-        return anz.circuit(full(free))
-
-    def u_func(free):
-        free = np.asarray(free)
-        dt = torch.float64 if free.dtype == np.float64 else torch.float32
-        return prog.unitary(torch.as_tensor(free[None].astype(free.dtype if free.dtype in (np.float32, np.float64)
-                                                               else np.float32)).to('cuda', dt))[0].cpu().numpy()
-
-    u_func.program = prog
-    u_func.fixed_params = projected_cp_angles
-    u_func.indices = projected_indices
+    circ_func, u_func = _constrained_funcs(anz, projected_cp_angles, projected_indices)
     return [circ_func, u_func, free_angles]
 
 
@@ -150,7 +134,7 @@ def filter_cp_results(res_list, cp_mask, threshold_cz_count, threshold_loss, thr
     return selected
 
 
-def verify_cp_results(results, anz, unitary_loss_func, options, keep_history=False):
+def verify_cp_results(results, anz, unitary_loss_func, options, keep_history=False, dtype=None, device=None):
     """Batched verify_cp_result (cp_utils.py:205-247) for a list of result dicts: project the CP
     angles at each best point, freeze them, and run Adam (no penalty) on the loss from the projected
     point — one fused launch for all candidates.  Returns a list of tuples
@@ -168,7 +152,12 @@ def verify_cp_results(results, anz, unitary_loss_func, options, keep_history=Fal
         bi = int(torch.argmin(regloss)) if isinstance(regloss, torch.Tensor) else int(np.argmin(regloss))
         p = res['params'][bi]
         picks.append(p if isinstance(p, torch.Tensor) else torch.as_tensor(np.asarray(p)))
-    angles = torch.stack([p.to('cuda', torch.float32) for p in picks]).contiguous()
+    # dtype / device: the caller's (Synthesize passes its own), else those of the stored parameters
+    if dtype is None:
+        dtype = picks[0].dtype if picks[0].dtype in (torch.float32, torch.float64) else torch.float32
+    if device is None:
+        device = picks[0].device if picks[0].is_cuda else torch.device('cuda', torch.cuda.current_device())
+    angles = torch.stack([p.to(device, dtype) for p in picks]).contiguous()
     cz, proj, frozen = prog.count_cz(angles, options.threshold_cp, project=True)
     raw = run_adam_batch(prog, unitary_loss_func, None, proj, options.learning_rate_at_verification,
                          options.num_gd_iterations_at_verification, freeze=frozen, keep_history=False)
@@ -188,20 +177,41 @@ def verify_cp_results(results, anz, unitary_loss_func, options, keep_history=Fal
     return out
 
 
+class _Constrained:
+    """`constrained_function(f, fixed_params, indices)` of the reference (cp_utils.py:100-108) as a picklable
+    top-level callable: f applied to the full angle vector with `fixed_params` inserted at `indices`.  The
+    reference stores local closures in `Decomposition._cp_data`; those need dill to be saved."""
+
+    def __init__(self, anz, fixed_params, indices):
+        self.anz = anz
+        self.fixed_params = np.asarray(fixed_params)
+        self.indices = [int(i) for i in indices]
+
+    def full(self, free):
+        return insert_params(np.asarray(free), self.fixed_params, self.indices)
+
+
+class ConstrainedCircuit(_Constrained):
+    def __call__(self, free):
+        return self.anz.circuit(self.full(free))
+
+
+class ConstrainedUnitary(_Constrained):
+    def __call__(self, free):
+        full = self.full(free)
+        return self.anz.unitary(full.astype(np.float64 if full.dtype == np.float64 else np.float32))
+
+    @property
+    def program(self):
+        """The constant-folded gate program over the free angles (Ansatz.constrained)."""
+        return self.anz.constrained(self.fixed_params, self.indices)[0]
+
+
 def _constrained_funcs(anz, fixed_val, fixed_idx):
-    def full(free):
-        return insert_params(np.asarray(free), fixed_val, fixed_idx)
-
-    def circ_func(free):
-        return anz.circuit(full(free))
-
-    def u_func(free):
-        return anz.unitary(full(free).astype(np.float32))
-
-    u_func.fixed_params, u_func.indices = fixed_val, fixed_idx
-    return circ_func, u_func
+    return ConstrainedCircuit(anz, fixed_val, fixed_idx), ConstrainedUnitary(anz, fixed_val, fixed_idx)
 
 
-def verify_cp_result(res, anz, unitary_loss_func, options, keep_history=False):
+def verify_cp_result(res, anz, unitary_loss_func, options, keep_history=False, dtype=None, device=None):
     """cp_utils.py:205-247 for one result: (success, num_cz_gates, circ, u, best_angs)."""
-    return verify_cp_results([res], anz, unitary_loss_func, options, keep_history=keep_history)[0]
+    return verify_cp_results([res], anz, unitary_loss_func, options, keep_history=keep_history, dtype=dtype,
+                             device=device)[0]

@@ -74,16 +74,16 @@ __device__ __forceinline__ void apply_grad(const KParams<R>& p, bool active, lon
     if (active) p.grad_out[b * P + pi] = g;
     return;
   }
-  if (frz && frz[pi]) return;
-  const R mu0 = gi == 0 ? R(0) : mom[pi];
-  const R nu0 = gi == 0 ? R(0) : vel[pi];
-  const AdamOut<R> o = adam_step(g, th, mu0, nu0, p.b1, p.omb1, p.b2, p.omb2, bc1, bc2, p.eps, -p.lr);
-  th = o.th;
-  if (active) {
-    mom[pi] = o.mu; vel[pi] = o.nu; ang[pi] = th;
-    if (p.hist_params && gi + 1 < p.hist_len)
-      p.hist_params[(b * p.hist_len + gi + 1) * P + pi] = th;
+  // a frozen parameter skips the Adam update only: its (unchanged) value still goes into the history row
+  if (!(frz && frz[pi])) {
+    const R mu0 = gi == 0 ? R(0) : mom[pi];
+    const R nu0 = gi == 0 ? R(0) : vel[pi];
+    const AdamOut<R> o = adam_step(g, th, mu0, nu0, p.b1, p.omb1, p.b2, p.omb2, bc1, bc2, p.eps, -p.lr);
+    th = o.th;
+    if (active) { mom[pi] = o.mu; vel[pi] = o.nu; ang[pi] = th; }
   }
+  if (active && p.hist_params && gi + 1 < p.hist_len)
+    p.hist_params[(b * p.hist_len + gi + 1) * P + pi] = th;
 }
 
 // resident CTAs per SM the register allocator is asked to allow for (state registers per thread

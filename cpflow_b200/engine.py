@@ -20,6 +20,12 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _on(t):
+    """Context that makes `t`'s device current: the C side launches on the current device (its per-device program
+    tables, `cudaGetDevice`) and `_stream()` is torch's current stream OF that device."""
+    return torch.cuda.device(t.device)
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not (t.is_cuda and t.is_contiguous()):
@@ -79,7 +85,8 @@ class Program:
         B = angles.shape[0]
         N = self.dim
         out = torch.empty(B, N, N, dtype=_CDT[angles.dtype], device=angles.device)
-        L.check(L.load().cpf_unitary(self._h, _DT[angles.dtype], B, _ptr(angles), _ptr(out), _stream()))
+        with _on(angles):
+            L.check(L.load().cpf_unitary(self._h, _DT[angles.dtype], B, _ptr(angles), _ptr(out), _stream()))
         return out
 
     def loss_grad(self, angles, loss, penalty=None, want_grad=True):
@@ -91,16 +98,18 @@ class Program:
         gr = torch.empty(B, self.n_params, dtype=dt, device=angles.device) if want_grad else None
         ls = loss.spec(dt, angles.device)
         ps = penalty.spec() if penalty is not None else None
-        L.check(L.load().cpf_loss_grad(self._h, C.byref(ls), C.byref(ps) if ps is not None else None,
-                                       _DT[dt], B, _ptr(angles), _ptr(lo), _ptr(rg), _ptr(gr), _stream()))
+        with _on(angles):
+            L.check(L.load().cpf_loss_grad(self._h, C.byref(ls), C.byref(ps) if ps is not None else None,
+                                           _DT[dt], B, _ptr(angles), _ptr(lo), _ptr(rg), _ptr(gr), _stream()))
         return lo, rg, gr
 
     def adjoint_from_cotangent(self, angles, cotangent):
         _need_cuda(angles, cotangent)
         B = angles.shape[0]
         gr = torch.empty(B, self.n_params, dtype=angles.dtype, device=angles.device)
-        L.check(L.load().cpf_adjoint_from_cotangent(self._h, _DT[angles.dtype], B, _ptr(angles),
-                                                    _ptr(cotangent), _ptr(gr), _stream()))
+        with _on(angles):
+            L.check(L.load().cpf_adjoint_from_cotangent(self._h, _DT[angles.dtype], B, _ptr(angles),
+                                                        _ptr(cotangent), _ptr(gr), _stream()))
         return gr
 
     def count_cz(self, angles, threshold=0.2, project=False):
@@ -109,8 +118,9 @@ class Program:
         cz = torch.empty(B, dtype=torch.int32, device=angles.device)
         proj = torch.empty_like(angles) if project else None
         frozen = torch.empty(B, self.n_params, dtype=torch.uint8, device=angles.device) if project else None
-        L.check(L.load().cpf_count_cz(self._h, _DT[angles.dtype], B, _ptr(angles), float(threshold),
-                                      _ptr(cz), _ptr(proj), _ptr(frozen), _stream()))
+        with _on(angles):
+            L.check(L.load().cpf_count_cz(self._h, _DT[angles.dtype], B, _ptr(angles), float(threshold),
+                                          _ptr(cz), _ptr(proj), _ptr(frozen), _stream()))
         return (cz, proj, frozen) if project else cz
 
     def initial_angles(self, seed, total_samples, first=0, count=None, cp_dist="uniform",
@@ -135,9 +145,10 @@ class Program:
         ps = penalty.spec() if penalty is not None else None
         ad = L.CpfAdamSpec(float(lr), float(b1), float(b2), float(eps))
         buf = state.buffers()
-        L.check(L.load().cpf_adam_run(self._h, C.byref(ls), C.byref(ps) if ps is not None else None,
-                                      C.byref(ad), _DT[dt], state.batch, state.step, int(num_steps),
-                                      C.byref(buf), _stream()))
+        with _on(state.angles):
+            L.check(L.load().cpf_adam_run(self._h, C.byref(ls), C.byref(ps) if ps is not None else None,
+                                          C.byref(ad), _DT[dt], state.batch, state.step, int(num_steps),
+                                          C.byref(buf), _stream()))
         state.step += int(num_steps)
         return state
 
@@ -161,7 +172,8 @@ class AdamState:
         self.init_regloss = torch.empty(B, dtype=dt, device=dev)
         self.init_reg = torch.empty(B, dtype=dt, device=dev)
         self.hist_len = int(hist_len)
-        self.hist_params = torch.zeros(B, hist_len, P, dtype=dt, device=dev) if hist_len else None
+        # rows start as the initial angles: parameters that feed no gate are never written by the kernels
+        self.hist_params = angles[:, None, :].repeat(1, hist_len, 1).contiguous() if hist_len else None
         self.hist_regloss = torch.zeros(B, hist_len, dtype=dt, device=dev) if hist_len else None
         self.step = 0
 

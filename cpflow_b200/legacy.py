@@ -2,9 +2,11 @@
 
 The reference saves `Results` objects with dill (main.py:448-456); the files name cpflow, qiskit, hyperopt and
 jax classes and carry pickled lambdas (the loss closure).  None of those packages is needed here and nothing
-in the file is executed: the reader below resolves every class outside a small allow-list (builtins,
-collections, numpy) to an inert placeholder that only records constructor arguments and state, then copies the
-plain data out:
+in the file is executed: the reader below resolves every global outside an explicit (module, name) allow-list of
+plain data constructors (list / dict / complex ..., OrderedDict, numpy's array reconstructors) to an inert
+placeholder that only records constructor arguments and state, then copies the plain data out.  In particular
+`builtins.eval / exec / __import__ / getattr`, `functools.partial`, `copyreg`, `os.*` all become placeholders, so a
+crafted file cannot run code through this reader:
 
 * every stored `Decomposition` -> `Decomposition` of this package: gate list -> `circuit.Circuit`, stored
   unitary / loss / type / CZ and T counts taken as stored (nothing is re-evaluated, so no GPU is needed);
@@ -25,7 +27,16 @@ import pickle
 
 import numpy as np
 
-_ALLOWED_MODULES = {"builtins", "collections", "copyreg", "_codecs", "functools", "fractions", "datetime"}
+# Explicit allow-list of globals a reference result file may really resolve: plain data constructors only.
+_ALLOWED = {
+    ("builtins", n) for n in ("list", "dict", "set", "frozenset", "tuple", "complex", "bytearray", "bytes", "slice",
+                              "range", "int", "float", "bool", "str", "object")
+} | {("collections", "OrderedDict"), ("collections", "defaultdict"), ("collections", "deque"),
+     ("fractions", "Fraction"), ("_codecs", "encode"),
+     ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy", "float32"), ("numpy", "float64"), ("numpy", "int32"),
+     ("numpy", "int64"), ("numpy", "complex64"), ("numpy", "complex128"), ("numpy", "bool_"),
+     ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"),
+     ("numpy._core.numeric", "_frombuffer")}
 
 
 class _Inert:
@@ -57,10 +68,10 @@ class _Reader(pickle.Unpickler):
         self._classes = {}
 
     def find_class(self, module, name):
-        if module in _ALLOWED_MODULES:
+        if module.startswith("numpy.core"):                      # numpy 1 paths in the stored files
+            module = module.replace("numpy.core", "numpy._core", 1)
+        if (module, name) in _ALLOWED:
             return super().find_class(module, name)
-        if module == "numpy" or module.startswith("numpy."):
-            return super().find_class(module.replace("numpy.core", "numpy._core"), name)
         if module.startswith("dill"):
             # dill's reconstruction helpers (_create_function, _create_cell, _load_type, _get_attr, ...) are
             # CALLED by the pickle: return a factory that yields a fresh inert class holding the call's arguments

@@ -17,17 +17,21 @@ import torch
 
 from . import parallel as PL
 from .ansatz import Ansatz
-from .circuit import convert_to_ZXZ, cp_to_cz_circuit, gates_count, gates_depth
+from .circuit import convert_to_ZXZ, cp_template_cz_count_depth, cp_to_cz_circuit, gates_count, gates_depth
 from .cp_utils import (filter_cp_results, random_cp_angles, select_batch, verify_cp_result, verify_cp_results)
 from .engine import Loss, Penalty
 from .optimization import ProgramLoss, RawResults, mynimize_repeated, run_adam_batch
 from .penalty import PenaltyFunction, RegularizationOptions, make_regularization_function
+from .matrix_utils import theoretical_lower_bound
 from .topology import fill_layers, num_qubits_from_layer
 
-try:  # the reference saves with dill; plain pickle is enough for our spec-based objects
+try:  # the reference saves with dill; user-supplied callables (a custom unitary_loss_func) need it to be saved
     import dill as _pickler
-except ImportError:  # pragma: no cover
+except ImportError:  # pragma: no cover - spec-based objects (Loss, PenaltyFunction, options, circuits) pickle plainly
     _pickler = pickle
+
+# first bytes of a file written by Results.save(): tells our own files from the reference's dill files
+_MAGIC = b'CPFLOW_B200_RESULTS\x01\n'
 
 try:
     from tqdm import tqdm
@@ -36,9 +40,19 @@ except ImportError:  # pragma: no cover
         return x
 
 
-def theoretical_lower_bound(n):
-    """matrix_utils.py:11-14: CNOT-count lower bound (4^n - 3n - 1) / 4 for n-qubit unitaries."""
-    return int((4 ** n - 3 * n - 1) / 4 + 1)
+def batched_unitary_loss(unitary_loss_func, U):
+    """`unitary_loss_func` on a batch U [B,N,N] of device unitaries -> numpy [B].  Declarative `Loss` specs are
+    evaluated vectorised on the device with the formulas of `Loss.__call__` (matrix_utils.py:35-42 and the
+    tutorial's state / relative-phase losses); any other callable is applied to each unitary in turn."""
+    if isinstance(unitary_loss_func, Loss):
+        tgt = torch.as_tensor(unitary_loss_func.target).to(U.device, U.dtype)
+        n = U.shape[-1]
+        if unitary_loss_func.kind == 'hs':
+            return (1 - (U * tgt.conj()).sum((-1, -2)).abs() ** 2 / n ** 2).cpu().numpy()
+        if unitary_loss_func.kind == 'state':
+            return (1 - (tgt.conj() * U[:, :, 0]).sum(-1).abs() ** 2).cpu().numpy()
+        return (1 - ((tgt.conj() * U).abs() ** 2).sum((-1, -2)) / n).cpu().numpy()
+    return np.array([float(unitary_loss_func(u)) for u in U.cpu().numpy()])
 
 
 class Decomposition:
@@ -47,23 +61,49 @@ class Decomposition:
     Attributes mirror the reference: unitary_loss_func, circuit, unitary, label, loss, type,
     cz_count, cz_depth, t_count, t_depth and the provenance fields _cp_data, _static_options,
     _adaptive_options, _decomposer.
+
+    Decompositions made by `Synthesize.static()` come out of ONE batched device evaluation
+    (`_from_cp_batch`): unitary, loss and CZ count are there at once; the gate-list `circuit` (CP -> CZ
+    rewriting, ZXZ merging: host Python, ~1 ms each) is built on first access.
     """
 
     def __init__(self, unitary_loss_func, circuit, label='', type='Approximate'):
         self.unitary_loss_func = unitary_loss_func
-        self.circuit = circuit
+        self._circuit = circuit
         self.unitary = circuit.unitary()                 # evaluated by the CUDA engine (cpf_unitary)
         self.label = label
         self.loss = self.unitary_loss_func(self.unitary)
         self.type = type
-        self.cz_count = gates_count(['cz'], self.circuit)
-        self.cz_depth = gates_depth(['cz'], self.circuit)
+        self.cz_count = gates_count(['cz'], circuit)
+        self._cz_depth = gates_depth(['cz'], circuit)
         self.t_count = None
         self.t_depth = None
         self._cp_data = None
         self._static_options = None
         self._adaptive_options = None
         self._decomposer = None
+
+    # ---- lazily materialised fields ----
+    @property
+    def circuit(self):
+        if self.__dict__.get('_circuit') is None:
+            u_func, circ_func, angles = self._cp_data
+            self._circuit = convert_to_ZXZ(cp_to_cz_circuit(circ_func(angles), cp_threshold=1e-6))
+        return self._circuit
+
+    @circuit.setter
+    def circuit(self, qc):
+        self._circuit = qc
+
+    @property
+    def cz_depth(self):
+        if self.__dict__.get('_cz_depth') is None:
+            self._cz_depth = gates_depth(['cz'], self.circuit)
+        return self._cz_depth
+
+    @cz_depth.setter
+    def cz_depth(self, v):
+        self._cz_depth = v
 
     @classmethod
     def _from_cp_circuit(cls, unitary_loss_func, u_func, circ_func, angles, label):
@@ -74,6 +114,48 @@ class Decomposition:
         d = cls(unitary_loss_func, qc, label=label)
         d._cp_data = [u_func, circ_func, angles]
         return d
+
+    @classmethod
+    def _from_cp_batch(cls, unitary_loss_func, anz, full_angles, frozen, label='', device=None):
+        """`_from_cp_circuit` for a whole batch of verified results in one device pass.  full_angles [B,P]: the
+        template's angle vectors (projected CP angles already inserted); frozen [B,P] bool: which entries are the
+        fixed ones (`constrained_function`, cp_utils.py:100-108).  The CZ circuit of main.py:283-286 is the CP
+        template with CP(0) dropped, CP(pi) -> CZ and every other CP -> two CZ (exact_decompositions.py:42-74,
+        threshold 1e-6), so its unitary is the template's up to a global phase: ONE batched cpf_unitary in
+        complex128 gives every `unitary`, the losses are evaluated on that batch, CZ count and depth follow from
+        the CP angles, and the gate list is built when `circuit` is first read."""
+        from .cp_utils import _constrained_funcs
+        full_angles = np.asarray(full_angles)
+        frozen = np.asarray(frozen, dtype=bool)
+        B = len(full_angles)
+        if B == 0:
+            return []
+        dev = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        a64 = torch.as_tensor(full_angles.astype(np.float64)).to(dev).contiguous()
+        U = anz.program.unitary(a64)
+        losses = batched_unitary_loss(unitary_loss_func, U)
+        U = U.cpu().numpy()
+        cp_idx = np.flatnonzero(np.asarray(anz.cp_mask) == 1)
+        cz_count, cz_depth = cp_template_cz_count_depth(anz.all_placements, full_angles[:, cp_idx], anz.num_qubits)
+        out = []
+        for b in range(B):
+            fixed_idx = np.flatnonzero(frozen[b])
+            free = full_angles[b][~frozen[b]]
+            circ_func, u_func = _constrained_funcs(anz, full_angles[b][fixed_idx], fixed_idx)
+            d = object.__new__(cls)
+            d.unitary_loss_func = unitary_loss_func
+            d._circuit = None
+            d.unitary = U[b]
+            d.label = label
+            d.loss = float(losses[b])
+            d.type = 'Approximate'
+            d.cz_count = int(cz_count[b])
+            d._cz_depth = int(cz_depth[b])
+            d.t_count = d.t_depth = None
+            d._cp_data = [u_func, circ_func, free]
+            d._static_options = d._adaptive_options = d._decomposer = None
+            out.append(d)
+        return out
 
     def refine(self, max_denominator=32, angle_threshold=0.01, cp_threshold=0.01, reduce_threshold=1e-5,
                recursion_degree=0, recursion_depth=5):
@@ -171,23 +253,32 @@ class Results:
             self.save_to = f'results/{self.label}'
 
     def save(self):
+        """main.py:459-462.  Written to a temporary file and renamed, so an interrupted `adaptive()` run never
+        leaves a truncated file behind."""
         os.makedirs(os.path.dirname(self.save_to) or '.', exist_ok=True)
-        with open(self.save_to, 'wb') as f:
-            _pickler.dump(self, f)
+        tmp = f'{self.save_to}.tmp{os.getpid()}'
+        try:
+            with open(tmp, 'wb') as f:
+                f.write(_MAGIC)
+                _pickler.dump(self, f)
+            os.replace(tmp, self.save_to)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
 
     @staticmethod
     def load(path):
-        """main.py:458-461.  Files written by the reference itself (they name cpflow / qiskit / hyperopt / jax
-        classes that are not installed here) are read through `legacy.load_reference_results`."""
-        try:
-            with open(path, 'rb') as f:
+        """main.py:464-469.  Files written by this package start with a magic line and are unpickled (with dill
+        when installed): like any pickle, only load files you trust.  Anything else is taken for a file written by
+        the reference itself (it names cpflow / qiskit / hyperopt / jax classes that are not installed here) and
+        goes through `legacy.load_reference_results`, which executes nothing from the file."""
+        with open(path, 'rb') as f:
+            head = f.read(len(_MAGIC))
+            if head == _MAGIC:
                 res = _pickler.load(f)
-            if isinstance(res, Results):
+                if not isinstance(res, Results):
+                    raise TypeError(f'{path}: holds a {type(res).__name__}, not a Results object')
                 return res
-        except FileNotFoundError:
-            raise
-        except Exception:      # ModuleNotFoundError / AttributeError of a foreign class path, dill helpers, ...
-            pass
         from .legacy import load_reference_results
         return load_reference_results(path)
 
@@ -387,16 +478,14 @@ class Synthesize:
             else:
                 out = torch.zeros(0, 2 + 2 * P, dtype=torch.float64, device=dev)
             out = PL.gather_round_robin(out, len(cand)).cpu().numpy()
-            from .cp_utils import _constrained_funcs
-            for row in tqdm(out, disable=rank != 0):
-                best_loss, num_cz = row[0], int(row[1])
-                if not best_loss <= options.target_loss:
-                    continue
-                full = row[2:2 + P].astype(np.float32 if self.dtype == torch.float32 else np.float64)
-                frozen_idx = [int(i) for i in np.flatnonzero(row[2 + P:] > 0.5)]
-                free_idx = [i for i in range(P) if i not in set(frozen_idx)]
-                circ, u = _constrained_funcs(anz, full[frozen_idx], frozen_idx)
-                successful_results.append(self._make_decomposition(u, circ, full[free_idx], static_options=options))
+            ok = out[:, 0] <= options.target_loss                    # cp_utils.py:245
+            np_dt = np.float32 if self.dtype == torch.float32 else np.float64
+            successful_results = Decomposition._from_cp_batch(
+                self.unitary_loss_func, anz, out[ok, 2:2 + P].astype(np_dt), out[ok, 2 + P:] > 0.5,
+                label=self.label, device=dev)
+            for d in successful_results:
+                d._static_options = options
+                d._decomposer = self
             if successful_results:
                 say(f'\n{len(successful_results)} successful. cz counts are:')
                 say(sorted([d.cz_count for d in successful_results]))

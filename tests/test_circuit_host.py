@@ -157,3 +157,24 @@ def test_seed_chain_and_tpe(trials):
     early = np.mean([t["loss"] for t in res[:10]])
     late = np.mean([t["loss"] for t in res[-20:]])
     assert late < early   # proposals concentrate on the good region
+
+
+def test_batched_cz_count_and_depth_match_the_built_circuits():
+    """`cp_template_cz_count_depth` (used by Synthesize.static() for all verified results at once) against the
+    circuits built gate by gate (exact_decompositions.py:42-74, 280-290)."""
+    from cpflow_b200.ansatz import Ansatz
+    from cpflow_b200.topology import fill_layers
+    rng = np.random.default_rng(3)
+    for n, layer, K in [(3, [[0, 1], [1, 2]], 9), (4, [[0, 1], [0, 2], [0, 3]], 14), (4, [[3, 1], [2, 0], [1, 2]], 11)]:
+        anz = Ansatz(n, "cp", fill_layers(layer, K))
+        cp_idx = np.flatnonzero(anz.cp_mask)
+        A = rng.uniform(0, 2 * np.pi, (25, anz.num_angles)).astype(np.float32)
+        for b in range(25):
+            k = rng.choice(cp_idx, len(cp_idx) // 2, replace=False)
+            A[b, k] = rng.choice(np.array([0.0, np.pi], dtype=np.float32), len(k))
+        A[0, cp_idx[0]] = 5e-7          # inside the 1e-6 window
+        A[1, cp_idx[1]] = np.float32(2 * np.pi)   # NOT folded: the rule acts on the raw angle
+        cnt, dep = CI.cp_template_cz_count_depth(anz.all_placements, A[:, cp_idx], n)
+        for b in range(25):
+            qc = CI.convert_to_ZXZ(CI.cp_to_cz_circuit(anz.circuit(A[b]), 1e-6))
+            assert cnt[b] == CI.gates_count(["cz"], qc) and dep[b] == CI.gates_depth(["cz"], qc)

@@ -126,6 +126,16 @@ def test_static_ccz_readme_example(tmp_path):
         assert d.cz_count == d.circuit.count_ops()["cz"] and 1 <= d.cz_depth <= d.cz_count
         assert set(d.circuit.count_ops()) <= {"rz", "rx", "cz"}
         assert "CZ count" in repr(d) and d.type == "Approximate" and d._static_options is opts
+        # batched construction (one cpf_unitary for all verified results, lazy gate list) == the gate-list route
+        from cpflow_b200.circuit import gates_depth
+        assert d.cz_depth == gates_depth(["cz"], d.circuit)
+        assert hst(d.circuit.unitary(), d.unitary) < 1e-12
+        assert abs(d.loss - Loss("hs", CCZ)(d.circuit.unitary())) < 1e-12
+        u_func, circ_func, free = d._cp_data
+        assert hst(u_func(free).astype(complex), d.unitary) < 1e-5 and circ_func(free).count_ops()["cp"] == 12
+    import pickle
+    back = pickle.loads(pickle.dumps(res))           # plain pickle is enough (no closures in _cp_data)
+    assert [x.cz_count for x in back.decompositions] == [x.cz_count for x in res.decompositions]
     assert min(d.cz_count for d in res.decompositions) <= 8   # README shows an 8-CZ result
     back = cp.Results.load(str(tmp_path / "ccz"))
     assert len(back.decompositions) == len(res.decompositions)

@@ -139,3 +139,35 @@ def test_results_load_falls_back_to_the_reference_format(fake_reference_file, tm
     assert isinstance(back, Results) and back.label == "own" and back.best_hyperparameters() == [[3, 0.1]]
     with pytest.raises(FileNotFoundError):
         Results.load(str(tmp_path / "missing"))
+
+
+def test_reader_runs_nothing_from_a_crafted_file(tmp_path):
+    """A pickle that REDUCEs builtins.eval / os.system / functools.partial must not execute anything: every global
+    outside the explicit data allow-list becomes an inert placeholder (legacy.py: _ALLOWED)."""
+    import io
+    import pickle
+    from cpflow_b200 import legacy
+
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, (f"open({str(marker)!r}, 'w').write('x')",))
+
+    class Evil2:
+        def __reduce__(self):
+            import os
+            return (os.system, (f"touch {marker}",))
+
+    class Evil3:
+        def __reduce__(self):
+            import functools
+            return (functools.partial, (exec, f"open({str(marker)!r}, 'w')"))
+
+    for obj in (Evil(), Evil2(), Evil3(), [Evil(), {"a": Evil2()}]):
+        out = legacy._Reader(io.BytesIO(pickle.dumps(obj, protocol=4))).load()
+        assert not marker.exists()
+        assert "inert" in repr(out) or isinstance(out, list)
+    for name in ("eval", "exec", "__import__", "getattr", "compile", "open"):
+        assert ("builtins", name) not in legacy._ALLOWED
+    assert not any(m in ("functools", "copyreg", "os", "posix", "subprocess") for m, _ in legacy._ALLOWED)
