@@ -65,6 +65,8 @@ EXPORTS = {
     "cpf_adam_run": (C.c_int, [C.c_void_p, C.POINTER(CpfLossSpec), C.POINTER(CpfPenaltySpec),
                                C.POINTER(CpfAdamSpec), C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                C.POINTER(CpfAdamBuffers), C.c_void_p]),
+    "cpf_adam_step": (C.c_int, [C.c_void_p, C.POINTER(CpfPenaltySpec), C.POINTER(CpfAdamSpec), C.c_int32, C.c_int64,
+                                C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(CpfAdamBuffers), C.c_void_p]),
     "cpf_count_cz": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "cpf_cz_value": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),

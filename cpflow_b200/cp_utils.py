@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import Loss, _DT, _ptr, _stream
+from .engine import Loss, TorchLoss, _DT, _ptr, _stream
 from .optimization import RawResults, run_adam_batch
 
 
@@ -21,8 +21,8 @@ def random_cp_angles(anz, num_samples=1, cp_dist='uniform', seed=0, first=0, cou
     """Batch form of random_cp_angles (cp_utils.py:13-42) under Synthesize._generate_initial_angles
     (main.py:541-548): rows [first, first+count) of the `num_samples` vectors drawn from
     PRNGKey(seed) with jax 0.3.x threefry semantics.  Returns a CUDA tensor [count, P]."""
-    if cp_dist not in ('uniform', '0'):
-        raise NotImplementedError(f"cp_dist {cp_dist!r}: the device sampler implements 'uniform' and '0'")
+    if cp_dist not in ('uniform', '0', 'normal'):
+        raise ValueError(f"cp_dist {cp_dist!r} not supported")      # cp_utils.py:41-42 prints and returns None
     return anz.program.initial_angles(seed, num_samples, first=first, count=count, cp_dist=cp_dist,
                                       dtype=dtype, device=device)
 
@@ -143,8 +143,8 @@ def verify_cp_results(results, anz, unitary_loss_func, options, keep_history=Fal
         raise NotImplementedError("verify_cp_results keeps no history (the reference's static() never asks)")
     if not len(results):
         return []
-    if not isinstance(unitary_loss_func, Loss):
-        raise TypeError("unitary_loss_func must be a Loss spec")
+    if not isinstance(unitary_loss_func, (Loss, TorchLoss)):
+        raise TypeError("unitary_loss_func must be a Loss spec or a TorchLoss")
     prog = anz.program
     picks = []
     for res in results:

@@ -382,6 +382,58 @@ __global__ void cz_value_kernel(const R* angles, long long n, R threshold, int32
   }
 }
 
+// ---- one optimiser step for a loss evaluated outside the engine (cpf_adam_step) ----
+// One warp per sample: penalty and its gradient (main.py:563-564), best tracking with strict < on the pre-update
+// parameters (optimization.py:61-75), optax Adam (optimization.py:22-23), history rows (optimization.py:52-59).
+template <typename R>
+__global__ void adam_step_kernel(const cpf::PenaltyT<R> pen, const uint8_t* __restrict__ pen_mask, int P, long long B,
+                                 long long step, R lr, R b1, R b2, R eps, R omb1, R omb2, const R* __restrict__ loss,
+                                 const R* __restrict__ grad, R* angles, R* m, R* v, const uint8_t* __restrict__ freeze,
+                                 R* best_params, R* best_regloss, R* best_reg, R* init_regloss, R* init_reg,
+                                 R* hist_params, R* hist_regloss, long long hist_len) {
+  const long long b = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (b >= B) return;
+  const int lane = threadIdx.x;
+  const size_t off = (size_t)b * P;
+  R reg_part = R(0);
+  if (pen.kind != CPF_PEN_NONE && pen_mask)
+    for (int i = lane; i < P; i += 32)
+      if (pen_mask[i]) {
+        R val, slope;
+        cpf::penalty_eval(pen, angles[off + i], val, slope);
+        reg_part += val;
+      }
+  for (int d = 16; d >= 1; d >>= 1) reg_part += __shfl_xor_sync(0xffffffffu, reg_part, d);
+  const R reg = cpf::mul_rn(pen.kind != CPF_PEN_NONE ? pen.r : R(0), reg_part);
+  const R regloss = cpf::add_rn(loss[b], reg);
+  const bool improved = step == 0 || regloss < best_regloss[b];
+  __syncwarp();
+  if (lane == 0) {
+    if (step == 0) { init_regloss[b] = regloss; init_reg[b] = reg; }
+    if (improved) { best_regloss[b] = regloss; best_reg[b] = reg; }
+    if (hist_regloss && step < hist_len) hist_regloss[b * hist_len + step] = regloss;
+  }
+  const R bc1 = cpf::bias_corr(b1, R(step + 1)), bc2 = cpf::bias_corr(b2, R(step + 1));
+  for (int i = lane; i < P; i += 32) {
+    R th = angles[off + i];
+    if (improved) best_params[off + i] = th;
+    if (hist_params && step == 0) hist_params[(size_t)b * hist_len * P + i] = th;
+    if (!(freeze && freeze[off + i])) {
+      R g = grad[off + i];
+      if (pen.kind != CPF_PEN_NONE && pen_mask && pen_mask[i]) {
+        R val, slope;
+        cpf::penalty_eval(pen, th, val, slope);
+        g = cpf::add_rn(g, cpf::mul_rn(pen.r, slope));
+      }
+      const cpf::AdamOut<R> o = cpf::adam_step(g, th, step == 0 ? R(0) : m[off + i], step == 0 ? R(0) : v[off + i],
+                                               b1, omb1, b2, omb2, bc1, bc2, eps, -lr);
+      th = o.th;
+      m[off + i] = o.mu; v[off + i] = o.nu; angles[off + i] = th;
+    }
+    if (hist_params && step + 1 < hist_len) hist_params[((size_t)b * hist_len + step + 1) * P + i] = th;
+  }
+}
+
 // ---- jax 0.3.x threefry initial angles (main.py:541-548, cp_utils.py:13-42) ----
 __host__ __device__ inline void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
   const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
@@ -412,6 +464,35 @@ __host__ __device__ inline uint32_t threefry_iota(uint32_t k0, uint32_t k1, uint
   return x1;
 }
 
+// jax 0.3.x random.normal in float32 from 32 random bits: u = max(lo, f * (1 - lo) + lo) with lo = nextafter(-1, 0)
+// and f the uniform [0, 1) float of the bits, then sqrt(2) * erf_inv(u) with XLA's single-precision erf_inv
+// (Giles' polynomial approximation, xla/client/lib/math.cc: ErfInv32).  No reference artefact stores normal draws
+// ("parity unpinned"); the oracle restates the same arithmetic.
+__host__ __device__ inline float erfinv_xla_f32(float x) {
+  float w = -logf((1.0f - x) * (1.0f + x));
+  float p;
+  if (w < 5.0f) {
+    w = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w;
+    p = 0.00021858087f + p * w; p = -0.00125372503f + p * w; p = -0.00417768164f + p * w;
+    p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+  } else {
+    w = sqrtf(w) - 3.0f;
+    p = -0.000200214257f;
+    p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w;
+    p = 0.00573950773f + p * w; p = -0.0076224613f + p * w; p = 0.00943887047f + p * w;
+    p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+  }
+  return p * x;
+}
+__device__ inline float normal_from_bits(uint32_t bits) {
+  const float lo = -0.99999994f;                                      // nextafter(-1, 0)
+  const float f = __uint_as_float((bits >> 9) | 0x3f800000u) - 1.0f;
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, 2.0f), lo));       // float32(1 - lo) == 2
+  return __fmul_rn(1.41421354f, erfinv_xla_f32(u));
+}
+
 template <typename R>
 __global__ void initial_angles_kernel(const cpf::CpMeta* cp, int n_cp, int P, uint32_t seed_hi,
                                       uint32_t seed_lo, long long total, long long first,
@@ -419,7 +500,7 @@ __global__ void initial_angles_kernel(const cpf::CpMeta* cp, int n_cp, int P, ui
   const long long s = (long long)blockIdx.x;
   if (s >= count) return;
   const long long g = first + s;
-  __shared__ uint32_t sub[2];
+  __shared__ uint32_t sub[4];
   if (threadIdx.x == 0) {
     // key, *subkeys = split(PRNGKey(seed), total + 1); sample g uses subkeys[g] = row g + 1
     const uint32_t n1 = (uint32_t)(2 * (total + 1));
@@ -429,6 +510,12 @@ __global__ void initial_angles_kernel(const cpf::CpMeta* cp, int n_cp, int P, ui
     // key, subkey = split(k): subkey is row 1 of a (2,2) split (cp_utils.py:31)
     sub[0] = threefry_iota(a0, a1, 4, 2);
     sub[1] = threefry_iota(a0, a1, 4, 3);
+    if (cp_dist == 2) {
+      // second split, of the FIRST split's key half (row 0): its row 1 seeds random.normal (cp_utils.py:39)
+      const uint32_t k0 = threefry_iota(a0, a1, 4, 0), k1 = threefry_iota(a0, a1, 4, 1);
+      sub[2] = threefry_iota(k0, k1, 4, 2);
+      sub[3] = threefry_iota(k0, k1, 4, 3);
+    }
   }
   __syncthreads();
   const float two_pi = 6.2831855f;  // float32(2*pi)
@@ -442,10 +529,49 @@ __global__ void initial_angles_kernel(const cpf::CpMeta* cp, int n_cp, int P, ui
     __syncthreads();
     for (int k = threadIdx.x; k < n_cp; k += blockDim.x)
       if (cp[k].pidx >= 0) out[s * P + cp[k].pidx] = R(0);
+  } else if (cp_dist == 2) {
+    // 'normal' (cp_utils.py:38-40): key, subkey = split(key) once more, CP angles = 1.5 * random.normal(subkey, (P,))
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_cp; k += blockDim.x)
+      if (cp[k].pidx >= 0) {
+        const uint32_t bits = threefry_iota(sub[2], sub[3], (uint32_t)P, (uint32_t)cp[k].pidx);
+        out[s * P + cp[k].pidx] = (R)__fmul_rn(1.5f, normal_from_bits(bits));
+      }
   }
 }
 
 }  // namespace
+
+template <typename R>
+static int run_adam_step(const cpf::Program* prog, const cpf_penalty_spec* pen, const cpf_adam_spec* adam, int64_t batch,
+                         int64_t step, const void* loss, const void* grad, const cpf_adam_buffers* buf, cudaStream_t st) {
+  cpf::KParams<R> p;
+  std::memset(&p, 0, sizeof(p));
+  uint8_t* unused = nullptr;
+  // fill_penalty validates the spec and converts the table; the per-parameter mask is rebuilt here ([P], not [n_cp])
+  int rc = fill_penalty(prog, pen, p, &unused, st);
+  if (unused) cudaFreeAsync(unused, st);
+  if (rc) return rc;
+  uint8_t* mask_dev = nullptr;
+  if (p.pen.kind != CPF_PEN_NONE && prog->n_params > 0) {
+    std::string mask((size_t)prog->n_params, '\0');
+    for (int i = 0; i < prog->n_params; ++i)
+      mask[i] = prog->is_cp_param[i] && (!pen->cp_mask || pen->cp_mask[i]) ? 1 : 0;
+    CPF_CUDA(cudaMallocAsync((void**)&mask_dev, mask.size(), st));
+    CPF_CUDA(cudaMemcpyAsync(mask_dev, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
+  }
+  dim3 block(32, 8);
+  const unsigned grid = (unsigned)((batch + 7) / 8);
+  adam_step_kernel<R><<<grid, block, 0, st>>>(
+      p.pen, mask_dev, prog->n_params, batch, step, (R)adam->lr, (R)adam->b1, (R)adam->b2, (R)adam->eps,
+      (R)(1.0 - adam->b1), (R)(1.0 - adam->b2), (const R*)loss, (const R*)grad, (R*)buf->angles, (R*)buf->m, (R*)buf->v,
+      buf->freeze, (R*)buf->best_params, (R*)buf->best_regloss, (R*)buf->best_reg, (R*)buf->init_regloss,
+      (R*)buf->init_reg, (R*)buf->hist_params, (R*)buf->hist_regloss, buf->hist_len);
+  cudaError_t e = cudaGetLastError();
+  if (mask_dev) cudaFreeAsync(mask_dev, st);
+  if (e != cudaSuccess) return cuda_fail("adam_step_kernel", e);
+  return CPF_OK;
+}
 
 template <typename R>
 static int launch_plan_t(const cpf::Program* prog, const cpf_loss_spec_kind_only& lk, int64_t batch, int n_sm, int regs,
@@ -585,6 +711,21 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_p
                                    (cudaStream_t)stream)));
 }
 
+int cpf_adam_step(const cpf_program* prog, const cpf_penalty_spec* penalty, const cpf_adam_spec* adam, int32_t dtype,
+                  int64_t batch, int64_t step, const void* loss, const void* grad, const cpf_adam_buffers* buf,
+                  void* stream) {
+  if (!prog || !adam || !buf || batch < 0 || step < 0) return fail(CPF_ERR_INVALID, "NULL argument / negative size");
+  if (batch == 0) return CPF_OK;
+  if (!loss || !grad) return fail(CPF_ERR_INVALID, "loss / grad is NULL");
+  if (!buf->angles || !buf->m || !buf->v || !buf->best_params || !buf->best_regloss || !buf->best_reg ||
+      !buf->init_regloss || !buf->init_reg)
+    return fail(CPF_ERR_INVALID, "a required cpf_adam_buffers pointer is NULL");
+  if ((buf->hist_params || buf->hist_regloss) && buf->hist_len <= 0)
+    return fail(CPF_ERR_INVALID, "history buffers given with hist_len <= 0");
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  CPF_DISPATCH(dtype, (run_adam_step<R>(p, penalty, adam, batch, step, loss, grad, buf, (cudaStream_t)stream)));
+}
+
 int cpf_count_cz(const cpf_program* prog, int32_t dtype, int64_t batch, const void* angles, double threshold,
                  int32_t* cz_out, void* projected, uint8_t* frozen, void* stream) {
   if (!prog || batch < 0) return fail(CPF_ERR_INVALID, "NULL program / bad batch");
@@ -630,7 +771,7 @@ int cpf_initial_angles(const cpf_program* prog, int32_t dtype, uint64_t seed, in
                        int64_t first, int64_t count, int32_t cp_dist, void* out, void* stream) {
   if (!prog || !out || total_samples < 0 || first < 0 || count < 0 || first + count > total_samples)
     return fail(CPF_ERR_INVALID, "bad sample range");
-  if (cp_dist != 0 && cp_dist != 1) return fail(CPF_ERR_UNSUPPORTED, "cp_dist must be 0 ('uniform') or 1 ('0')");
+  if (cp_dist < 0 || cp_dist > 2) return fail(CPF_ERR_UNSUPPORTED, "cp_dist must be 0 ('uniform'), 1 ('0') or 2 ('normal')");
   if (2 * (total_samples + 1) > 0xffffffffLL) return fail(CPF_ERR_UNSUPPORTED, "too many samples for a 32-bit counter");
   if (count == 0) return CPF_OK;
   const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);

@@ -127,7 +127,7 @@ class Program:
                        dtype=torch.float32, device="cuda"):
         count = total_samples - first if count is None else count
         out = torch.empty(count, self.n_params, dtype=dtype, device=device)
-        code = {"uniform": 0, "0": 1}.get(cp_dist)
+        code = {"uniform": 0, "0": 1, "normal": 2}.get(cp_dist)
         if code is None:
             raise L.CpflowError(f"cp_dist {cp_dist!r} is not supported on the device sampler")
         with torch.cuda.device(out.device):
@@ -150,6 +150,22 @@ class Program:
                                           C.byref(ad), _DT[dt], state.batch, state.step, int(num_steps),
                                           C.byref(buf), _stream()))
         state.step += int(num_steps)
+        return state
+
+
+    def adam_step(self, state, loss_values, grad, penalty, lr, b1=0.9, b2=0.999, eps=1e-8):
+        """One iteration of the Adam loop for a loss evaluated outside the engine (cpf_adam_step): penalty, best
+        tracking and the Adam update on `state`, given loss_values [B] and grad [B,P] = d loss / d theta."""
+        _need_cuda(loss_values, grad)
+        dt = state.angles.dtype
+        ps = penalty.spec() if penalty is not None else None
+        ad = L.CpfAdamSpec(float(lr), float(b1), float(b2), float(eps))
+        buf = state.buffers()
+        with _on(state.angles):
+            L.check(L.load().cpf_adam_step(self._h, C.byref(ps) if ps is not None else None, C.byref(ad), _DT[dt],
+                                           state.batch, state.step, _ptr(loss_values), _ptr(grad), C.byref(buf),
+                                           _stream()))
+        state.step += 1
         return state
 
 
@@ -223,6 +239,54 @@ class Loss:
 
     def __repr__(self):
         return f"Loss({self.kind!r}, target{tuple(self.target.shape)})"
+
+
+class TorchLoss:
+    """An arbitrary user loss `unitary_loss_func(U)` (reference main.py:528-529) written with torch operations:
+    a function of ONE unitary (complex tensor [N,N]) returning a real scalar tensor.  It cannot run inside the
+    fused kernel, so the optimisation alternates cpf_unitary -> this function and its autograd cotangent ->
+    cpf_adjoint_from_cotangent -> cpf_adam_step (optimization.run_adam_batch); the Adam arithmetic, penalty, best
+    tracking and freeze masks are the engine's own."""
+
+    def __init__(self, fn):
+        if not callable(fn):
+            raise TypeError("unitary_loss_func must be a Loss spec or a callable of a torch unitary")
+        self.fn = fn
+        self._vmap_ok = None
+
+    def batch(self, U):
+        """Loss of every unitary of U [B,N,N] -> real tensor [B] (torch.vmap when the function allows it)."""
+        if self._vmap_ok is not False:
+            try:
+                out = torch.vmap(self.fn)(U)
+                self._vmap_ok = True
+                return out.real if out.is_complex() else out
+            except Exception:
+                if self._vmap_ok:
+                    raise
+                self._vmap_ok = False
+        out = torch.stack([torch.as_tensor(self.fn(u)) for u in U])
+        return out.real if out.is_complex() else out
+
+    def value_and_cotangent(self, U):
+        """loss [B] and dL/dconj(U) [B,N,N] (the seed of cpf_adjoint_from_cotangent): torch's gradient of a real
+        function with respect to a complex tensor is 2 dL/dconj(U)."""
+        U = U.detach().requires_grad_(True)
+        with torch.enable_grad():
+            loss = self.batch(U)
+            (g,) = torch.autograd.grad(loss.sum(), U)
+        return loss.detach(), (g / 2).contiguous()
+
+    def __call__(self, u):
+        """Value at one explicit unitary (numpy or torch) -> float."""
+        t = torch.as_tensor(np.asarray(u)) if not isinstance(u, torch.Tensor) else u
+        with torch.no_grad():
+            v = self.fn(t)
+        v = torch.as_tensor(v)
+        return float(v.real if v.is_complex() else v)
+
+    def __repr__(self):
+        return f"TorchLoss({getattr(self.fn, '__name__', self.fn)!r})"
 
 
 class Penalty:

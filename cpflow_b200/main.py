@@ -19,9 +19,9 @@ from . import parallel as PL
 from .ansatz import Ansatz
 from .circuit import convert_to_ZXZ, cp_template_cz_count_depth, cp_to_cz_circuit, gates_count, gates_depth
 from .cp_utils import (filter_cp_results, random_cp_angles, select_batch, verify_cp_result, verify_cp_results)
-from .engine import Loss, Penalty
+from .engine import Loss, Penalty, TorchLoss
 from .optimization import ProgramLoss, RawResults, mynimize_repeated, run_adam_batch
-from .penalty import PenaltyFunction, RegularizationOptions, make_regularization_function
+from .penalty import PenaltyFunction, RegularizationOptions, make_regularization_function, tabulate_penalty
 from .matrix_utils import theoretical_lower_bound
 from .topology import fill_layers, num_qubits_from_layer
 
@@ -52,6 +52,9 @@ def batched_unitary_loss(unitary_loss_func, U):
         if unitary_loss_func.kind == 'state':
             return (1 - (tgt.conj() * U[:, :, 0]).sum(-1).abs() ** 2).cpu().numpy()
         return (1 - ((tgt.conj() * U).abs() ** 2).sum((-1, -2)) / n).cpu().numpy()
+    if isinstance(unitary_loss_func, TorchLoss):
+        with torch.no_grad():
+            return unitary_loss_func.batch(U).cpu().numpy()
     return np.array([float(unitary_loss_func(u)) for u in U.cpu().numpy()])
 
 
@@ -320,12 +323,13 @@ class Synthesize:
 
     Args:
         layer: qubit connectivity, e.g. [[0, 1], [1, 2]].
-        unitary_loss_func: a `Loss` spec ('hs' | 'state' | 'relphase' with its target).  The reference
-            takes an arbitrary Python function of the unitary here; the CUDA engine needs the
-            declarative form.
+        unitary_loss_func: a `Loss` spec ('hs' | 'state' | 'relphase' with its target; runs inside the fused
+            kernel), or any function of the unitary written with torch operations (complex tensor [N,N] -> real
+            scalar), as in the reference; the latter runs through a host-driven loop around the engine's kernels.
         target_unitary: if given, the loss is the Hilbert-Schmidt distance to it (matrix_utils.py:35-42).
         label: name used in results / save path.
-        cp_regularization_func: `PenaltyFunction` for one CP angle (default: the 'linear' penalty).
+        cp_regularization_func: `PenaltyFunction` for one CP angle (default: the 'linear' penalty), or any
+            2 pi-periodic piecewise-linear callable R(a), which is tabulated.
     """
 
     def __init__(self, layer, unitary_loss_func=None, target_unitary=None, label=None, cp_regularization_func=None,
@@ -334,10 +338,11 @@ class Synthesize:
         self.num_qubits = num_qubits_from_layer(self.layer)
         self.target_unitary = None if target_unitary is None else np.asarray(target_unitary)
         if unitary_loss_func is not None:
-            if not isinstance(unitary_loss_func, Loss):
-                raise TypeError("unitary_loss_func must be a cpflow_b200 Loss spec, e.g. Loss('state', psi); "
-                                "arbitrary Python callables cannot run inside the CUDA engine")
-            self.unitary_loss_func = unitary_loss_func
+            # main.py:528-529: any function of the unitary.  A `Loss` spec runs inside the fused kernel; any other
+            # callable (written with torch operations on a complex [N,N] tensor) runs through the host-driven loop
+            # cpf_unitary -> loss / autograd cotangent -> cpf_adjoint_from_cotangent -> cpf_adam_step.
+            self.unitary_loss_func = unitary_loss_func if isinstance(unitary_loss_func, (Loss, TorchLoss)) \
+                else TorchLoss(unitary_loss_func)
         else:
             assert self.target_unitary is not None, 'Neither unitary loss function nor target unitary is provided.'
             assert self.target_unitary.shape == (2 ** self.num_qubits, 2 ** self.num_qubits), \
@@ -345,9 +350,11 @@ class Synthesize:
             self.unitary_loss_func = Loss('hs', self.target_unitary)
         self.label = label
         if cp_regularization_func:
-            if not isinstance(cp_regularization_func, PenaltyFunction):
-                raise TypeError("cp_regularization_func must be a PenaltyFunction (segment table or 'l1')")
-            self.cp_regularization_func = cp_regularization_func
+            # main.py:536-539: any callable R(a).  The kernels consume a segment table: a PenaltyFunction is used
+            # as is, any other callable is tabulated (penalty.tabulate_penalty raises with the fit error if it is
+            # not a periodic piecewise-linear function of at most 16 pieces).
+            self.cp_regularization_func = cp_regularization_func if isinstance(cp_regularization_func, PenaltyFunction) \
+                else tabulate_penalty(cp_regularization_func)
         else:
             self.cp_regularization_func = make_regularization_function(RegularizationOptions)
         self.dtype = dtype
@@ -544,6 +551,16 @@ class Synthesize:
             say(f'score: {-score}, cz counts of prospective results: {cz_counts}')
             result = {'loss': -score, 'status': 'ok', 'random_seed': random_seed, 'cz_counts': cz_counts,
                       'num_cp_gates': num_cp_gates, 'r': r, 'layer': self.layer}
+            if options.keep_logs:
+                # main.py:741-755: the prospective results themselves stay in the trial record, and their pickled
+                # form goes into `attachments` together with the options and the loss
+                evaluated = [[int(row[1]), {'params': row[4:].to(self.dtype).cpu().numpy()[None],
+                                             'loss': row[2:3].cpu().numpy(), 'regloss': row[3:4].cpu().numpy()}]
+                             for row in cand]
+                result['prospective_decompositions'] = evaluated
+                result['attachments'] = {'prospective_decompositions': _pickler.dumps(evaluated),
+                                         'static_options': _pickler.dumps(static_options),
+                                         'unitary_loss_func': _pickler.dumps(self.unitary_loss_func)}
             trials.results.append(result)
             results.trials = trials
             if save_results and rank == 0:
@@ -560,7 +577,8 @@ class Synthesize:
             if len(to_verify):
                 res_list = [{'params': row[4:][None].to(self.dtype), 'regloss': row[3:4], 'loss': row[2:3]}
                             for row in to_verify]
-                ver = verify_cp_results(res_list, anz, self.unitary_loss_func, options.get_static(None, None))
+                ver = verify_cp_results(res_list, anz, self.unitary_loss_func, options.get_static(None, None),
+                                        dtype=self.dtype, device=self._device())
                 for success, num_cz_gates, circ, u, best_angs in ver:
                     if success:
                         say(f'\nFound a new decomposition with {num_cz_gates} gates.')

@@ -17,16 +17,17 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import Loss, Penalty, Program
+from .engine import Loss, Penalty, Program, TorchLoss
 
 HISTORY_BYTES_LIMIT = 64 << 30
 
 
 @dataclass
 class ProgramLoss:
-    """The declarative form of `lambda angles: unitary_loss_func(u_func(angles))`."""
+    """The declarative form of `lambda angles: unitary_loss_func(u_func(angles))`: `loss` is a `Loss` spec (fused
+    kernel) or a `TorchLoss` wrapping an arbitrary torch function of the unitary (host-driven loop)."""
     program: Program
-    loss: Loss
+    loss: object
 
     @property
     def num_params(self):
@@ -93,7 +94,15 @@ def run_adam_batch(program, loss, penalty, initial_params, learning_rate, num_it
                                 "use keep_history=False (the reference default for static())")
     with torch.cuda.device(initial_params.device):
         st = program.adam_state(initial_params.clone(), freeze=freeze, hist_len=T if keep_history else 0)
-        program.adam_run(st, loss, penalty, learning_rate, T)
+        if isinstance(loss, TorchLoss):
+            # user loss outside the engine: the same loop, one iteration at a time (optimization.py:14-25, 61-75)
+            for _ in range(T):
+                U = program.unitary(st.angles)
+                values, cot = loss.value_and_cotangent(U)
+                grad = program.adjoint_from_cotangent(st.angles, cot)
+                program.adam_step(st, values.to(st.angles.dtype).contiguous(), grad, penalty, learning_rate)
+        else:
+            program.adam_run(st, loss, penalty, learning_rate, T)
         if keep_history:
             params_h, regloss_h = st.hist_params, st.hist_regloss
             if penalty is not None:

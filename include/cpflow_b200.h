@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CPF_VERSION 100 /* 0.1.0 */
+#define CPF_VERSION 200 /* 0.2.0 */
 #define CPF_MAX_QUBITS 7
 #define CPF_MAX_SEGMENTS 16
 
@@ -183,6 +183,16 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss,
                  int64_t batch, int64_t step0, int64_t num_steps, const cpf_adam_buffers* buf,
                  void* stream);
 
+/* One iteration of the same loop for a loss that is evaluated OUTSIDE the engine (an arbitrary user
+ * `unitary_loss_func(U)`, cpflow/main.py:528-529): the caller evaluates loss[B] on cpf_unitary's output and gets
+ * grad[B,P] = d loss / d theta from cpf_adjoint_from_cotangent; this call adds the penalty and its gradient
+ * (cpflow/main.py:563-564), tracks the best point (strict <, pre-update parameters; `step` == 0 initialises
+ * init_* / best_*), and applies the optax-Adam update (cpflow/optimization.py:14-25, 61-75) in place, honouring
+ * `freeze` and the history buffers exactly like cpf_adam_run.  `step` = number of steps already taken. */
+int cpf_adam_step(const cpf_program* prog, const cpf_penalty_spec* penalty, const cpf_adam_spec* adam,
+                  int32_t dtype, int64_t batch, int64_t step, const void* loss, const void* grad,
+                  const cpf_adam_buffers* buf, void* stream);
+
 /* cz[B] (int32) = count_cz(angles * cp_mask, threshold) (cpflow/cp_utils.py:45-67): per CP
  * parameter 0 if (a mod 2pi) is within `threshold` of 0 or 2pi, 1 if within of pi, else 2.
  * If `projected` (nullable [B,P]) and `frozen` (nullable uint8 [B,P]) are given they receive the
@@ -199,7 +209,7 @@ int cpf_cz_value(int32_t dtype, int64_t n, const void* angles, double threshold,
  * cpflow/cp_utils.py:13-42, cpflow/trigonometric_utils.py:35-38) with jax 0.3.x threefry
  * semantics: sample s of a batch of `total_samples` drawn from PRNGKey(seed).  Writes samples
  * [first, first+count) to out[count,P]; results do not depend on how the batch is sharded.
- * cp_dist: 0 = 'uniform', 1 = '0' (CP angles zeroed). */
+ * cp_dist: 0 = 'uniform', 1 = '0' (CP angles zeroed), 2 = 'normal' (CP angles 1.5 * N(0,1), cp_utils.py:38-40). */
 int cpf_initial_angles(const cpf_program* prog, int32_t dtype, uint64_t seed,
                        int64_t total_samples, int64_t first, int64_t count, int32_t cp_dist,
                        void* out, void* stream);

@@ -766,18 +766,51 @@ def random_angles(num_angles, key):
     return prng_uniform(key, num_angles, 0.0, 2 * PI)
 
 
+def erf_inv_f32(x):
+    """lax.erf_inv in float32 as XLA computes it (xla/client/lib/math.cc, ErfInv32: Giles' polynomial
+    approximation, jaxlib 0.3.x: w = -log((1-x)(1+x)); two degree-8 polynomials in w - 2.5 / sqrt(w) - 3).
+    Third-party arithmetic that is not under /root/reference: restated from the published algorithm; no reference
+    artefact stores normal draws ("parity unpinned" for cp_dist='normal', which the reference never uses by
+    default, main.py:360)."""
+    x = np.asarray(x, dtype=np.float32)
+    one = np.float32(1)
+    w = -np.log((one - x) * (one + x)).astype(np.float32)
+    lt = w < np.float32(5)
+    w = np.where(lt, w - np.float32(2.5), np.sqrt(np.maximum(w, 0)).astype(np.float32) - np.float32(3)).astype(np.float32)
+    c_lt = [2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503,
+            -0.00417768164, 0.246640727, 1.50140941]
+    c_gt = [-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613,
+            0.00943887047, 1.00167406, 2.83297682]
+    p = np.where(lt, np.float32(c_lt[0]), np.float32(c_gt[0])).astype(np.float32)
+    for a, b in zip(c_lt[1:], c_gt[1:]):
+        p = (np.where(lt, np.float32(a), np.float32(b)) + p * w).astype(np.float32)
+    return (p * x).astype(np.float32)
+
+
+def prng_normal(key, size):
+    """jax.random.normal(key, (size,), float32) of jax 0.3.x (_normal_real): u = uniform(key, minval=nextafter(-1, 0),
+    maxval=1); sqrt(2) * erf_inv(u)."""
+    lo = np.nextafter(np.float32(-1), np.float32(0))
+    u = prng_uniform(key, size, lo, 1.0)
+    return (np.float32(np.sqrt(2)) * erf_inv_f32(u)).astype(np.float32)
+
+
 def generate_initial_angles(seed, num_angles, cp_mask, cp_dist="uniform", batch_size=1):
-    """main.py:541-548 + cp_utils.py:13-42 ('uniform' and '0'; 'normal' needs erf_inv and is
-    handled by the caller)."""
+    """main.py:541-548 + cp_utils.py:13-42: 'uniform', '0' (CP angles zeroed) and 'normal' (CP angles
+    1.5 * random.normal from a second split of the sample's key, cp_utils.py:38-40)."""
     key = prng_key(seed)
     keys = prng_split(key, batch_size + 1)
     out = np.zeros((batch_size, num_angles), dtype=np.float32)
+    mask = np.asarray(cp_mask, dtype=np.float32)
     for b in range(batch_size):
-        sub = prng_split(keys[b + 1], 2)[1]
+        k1, sub = prng_split(keys[b + 1], 2)          # key, subkey = random.split(key)   cp_utils.py:31
         out[b] = random_angles(num_angles, sub)
+        if cp_dist == "normal":
+            sub2 = prng_split(k1, 2)[1]               # key, subkey = random.split(key)   cp_utils.py:39
+            out[b] = out[b] * (1 - mask) + np.float32(1.5) * prng_normal(sub2, num_angles) * mask
     if cp_dist == "0":
-        out = out * (1 - np.asarray(cp_mask, dtype=np.float32))[None]
-    elif cp_dist != "uniform":
+        out = out * (1 - mask)[None]
+    elif cp_dist not in ("uniform", "normal"):
         raise ValueError(cp_dist)
     return out
 

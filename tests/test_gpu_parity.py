@@ -143,6 +143,37 @@ def test_adam_history_and_freeze_f64():
     assert torch.equal(st.angles.cpu()[fm], a0[fm])   # frozen entries never move
 
 
+@pytest.mark.parametrize("kind,env", [("state", {}), ("hs", {"CPF_ENGINE": "adjoint"}), ("hs", {}),
+                                      ("hs", {"CPF_NO_LAYERED": "1"})])
+def test_history_with_freeze_mask(kind, env):
+    """keep_history=True together with a freeze mask: every history row carries the frozen parameters' (unchanged)
+    values, on the state-adjoint kernels (state loss, CPF_ENGINE=adjoint), the interpreter and the Heisenberg kernel
+    alike; `mynimize_repeated`'s 'reg' / 'loss' histories are then evaluated on complete rows."""
+    n, layer, K = 3, connected_layer(3), 5
+    anz, oanz, ops = setup(n, layer, K, "xyz")
+    B, T = 4, 25
+    a0 = torch.tensor(np.random.default_rng(11).uniform(0, 2 * np.pi, (B, anz.num_angles)))
+    fm = torch.zeros(B, anz.num_angles, dtype=torch.bool)
+    rng = np.random.default_rng(12)
+    for b in range(B):
+        fm[b, rng.choice(anz.num_angles, 9, replace=False)] = True
+    V = unitary_group.rvs(8, random_state=5)
+    tgt = V[:, 0].copy() if kind == "state" else V
+    res = O.mynimize_repeated(n, ops, kind, torch.tensor(tgt), a0, 0.05, T, oanz.cp_mask, 0.002,
+                              O.make_regularization_function(), keep_history=True, freeze_mask=fm)
+
+    def run():
+        st = anz.program.adam_state(a0.to(DEV).clone(), freeze=fm.to(torch.uint8).to(DEV).contiguous(), hist_len=T)
+        anz.program.adam_run(st, Loss(kind, tgt), pen(0.002), 0.05, T)
+        return st
+    st = _with_env(env, run)
+    hp = st.hist_params.cpu()
+    assert np.abs(hp.numpy() - np.stack([r["params"].numpy() for r in res])).max() < 1e-9
+    assert np.abs(st.hist_regloss.cpu().numpy() - np.stack([r["regloss"].numpy() for r in res])).max() < 1e-10
+    for b in range(B):      # frozen columns are constant over the whole history
+        assert torch.equal(hp[b][:, fm[b]], a0[b][fm[b]][None].expand(T, -1))
+
+
 def test_constrained_program_equals_freeze_mask():
     """Ansatz.constrained (constant-angle program over the free vector) and the freeze mask are the
     same computation."""

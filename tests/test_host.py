@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/cpflow_b200.h but not exported"
     assert set(syms) == set(L.EXPORTS), "ctypes table and header disagree"
-    assert lib.cpf_version() == 100
+    assert lib.cpf_version() == 200
 
 
 def test_struct_layouts_match_header():
@@ -238,3 +238,41 @@ def test_built_kernels_fit_the_planned_occupancy(lib):
             assert stack <= 32, (k, stack)
     c3 = [v for k, v in heis32.items() if "HeisSweepIfLi4ELi2ELi3ELy528ELy801" in k]
     assert c3 and c3[0][0] <= 120        # the bench kernel: 2 CTAs x 256 threads x regs <= 64 K with room
+
+
+def test_tabulate_penalty_callable():
+    """A callable cp_regularization_func (reference main.py:536-539) becomes the kernels' segment table, or is
+    rejected with the fit error."""
+    import math
+    import torch
+    from cpflow_b200.penalty import RegularizationOptions, make_regularization_function, tabulate_penalty
+    pf0 = make_regularization_function(RegularizationOptions)
+    pf = tabulate_penalty(lambda a: pf0(a))
+    x = np.random.default_rng(0).uniform(-20, 20, 50000)
+    assert len(pf.segments) == 9 and np.abs(pf(x) - pf0(x)).max() < 1e-12
+    assert np.abs(pf(x) - O.make_regularization_function()(torch.tensor(x)).numpy()).max() < 1e-12
+    tri = lambda a: np.abs((np.mod(a, 2 * math.pi) / math.pi) - 1)          # noqa: E731
+    assert len(tabulate_penalty(tri).segments) == 2
+    ramp = lambda a: float(min(math.fmod(a, 2 * math.pi), 1.0))             # noqa: E731  scalar-only callable
+    pr = tabulate_penalty(ramp, grid=1 << 12)
+    assert len(pr.segments) == 2 and abs(pr(0.5) - 0.5) < 1e-9 and abs(pr(4.0) - 1.0) < 1e-9
+    with pytest.raises(ValueError):
+        tabulate_penalty(lambda a: (np.mod(a, 2 * math.pi) > 2.0) * 1.0)    # a jump inside the period
+    for bad in (lambda a: np.sin(a) ** 2, lambda a: np.abs(a)):
+        with pytest.raises(ValueError, match="periodic|piecewise|pieces"):
+            tabulate_penalty(bad)
+
+
+def test_oracle_normal_sampler():
+    """cp_dist='normal' in the oracle (cp_utils.py:38-40): XLA's float32 erf_inv polynomial against scipy, moments of
+    the draws, and the non-CP angles untouched."""
+    from scipy.special import erfinv
+    x = np.linspace(-0.999999, 0.999999, 20001).astype(np.float32)
+    big = np.abs(x) > 1e-3
+    assert np.abs(O.erf_inv_f32(x)[big] / erfinv(x.astype(np.float64))[big] - 1).max() < 1e-6
+    mask = (np.arange(93) % 7 == 2).astype(int)
+    a = O.generate_initial_angles(0, 93, mask, cp_dist="normal", batch_size=1500)
+    u = O.generate_initial_angles(0, 93, mask, cp_dist="uniform", batch_size=1500)
+    cp_draws = a[:, mask == 1]
+    assert abs(cp_draws.mean()) < 0.05 and abs(cp_draws.std() - 1.5) < 0.05
+    assert np.array_equal(a[:, mask == 0], u[:, mask == 0])
