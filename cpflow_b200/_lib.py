@@ -82,7 +82,7 @@ class CpfLaunchInfo(C.Structure):
     """cpf_launch_info (include/cpflow_b200.h)."""
     _fields_ = [("engine", C.c_int32), ("ctas_per_sm", C.c_int32), ("block_threads", C.c_int32),
                 ("samples_per_cta", C.c_int32), ("threads_per_sample", C.c_int32), ("max_block_threads", C.c_int32),
-                ("words_per_sample", C.c_int32), ("reserved", C.c_int32), ("grid", C.c_int64), ("smem_bytes", C.c_int64)]
+                ("words_per_sample", C.c_int32), ("time_slices", C.c_int32), ("grid", C.c_int64), ("smem_bytes", C.c_int64)]
 
 
 _lib = None

@@ -575,7 +575,7 @@ static int run_adam_step(const cpf::Program* prog, const cpf_penalty_spec* pen, 
 
 template <typename R>
 static int launch_plan_t(const cpf::Program* prog, const cpf_loss_spec_kind_only& lk, int64_t batch, int n_sm, int regs,
-                         cpf_launch_info* out) {
+                         cpf_launch_info* out, int adam_steps = 2000) {
   cpf_loss_spec ls{};
   ls.kind = lk.kind;
   const bool heis = use_heis<R>(prog, &ls) && (unsigned long long)batch * (unsigned long long)prog->n_params < (1ull << 32);
@@ -584,7 +584,13 @@ static int launch_plan_t(const cpf::Program* prog, const cpf_loss_spec_kind_only
   const int n = prog->n_qubits, N = 1 << n, cpt = cpf::heis_cpt<R>(n), tps = N / cpt;
   const int maxt = 2 * N * cpt * (int)(sizeof(R) / 4) <= 64 ? 512 : 256;          // HCfg::MAXT
   const int n_su2 = (int)prog->su2.size(), n_cp = (int)prog->cp.size();
-  const int n_stage = 2 * prog->period > n ? 2 * prog->period : n;                // HeisSweep::NSTAGE
+  int n_stage = n;                                                                // SWP::NSTAGE of the kernel chosen
+  {
+    cpf::KParams<R> dummy;
+    std::string e2;
+    int rc2 = 0;
+    cpf::launch_heis<R>(dummy, *prog, nullptr, e2, rc2, true, &n_stage);
+  }
   const int stride = cpf::heis_coef_stride(n_su2, n_cp, n_stage);
   const size_t target = (((size_t)cpf::heis_target_words<R>(n, cpt) * sizeof(R)) + 15) & ~(size_t)15;
   const cpf::HeisGeometry g = cpf::heis_geometry(batch, target + cpf::heis_meta_bytes(n_su2, n_cp),
@@ -593,6 +599,10 @@ static int launch_plan_t(const cpf::Program* prog, const cpf_loss_spec_kind_only
   out->ctas_per_sm = g.ctas; out->block_threads = g.block; out->samples_per_cta = g.spb; out->grid = g.grid;
   out->smem_bytes = (int64_t)g.smem; out->threads_per_sample = tps; out->max_block_threads = maxt;
   out->words_per_sample = stride;
+  // time slices an Adam run of `adam_steps` iterations over this batch would be cut into (1 = one launch)
+  out->time_slices = cpf::heis_slicing(batch, adam_steps > 0 ? adam_steps : 2000, target + cpf::heis_meta_bytes(n_su2, n_cp),
+                                       (size_t)stride * sizeof(R), tps, maxt, regs > 0 ? regs : 128,
+                                       n_sm > 0 ? n_sm : 148, true).k;
   return CPF_OK;
 }
 

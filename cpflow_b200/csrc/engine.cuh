@@ -63,6 +63,10 @@ struct KParams {
   int coef_stride;  // R words per sample in shared memory
   int spb;          // heis_kernel: sample slots used per CTA
   int sync_sweeps;  // heis_kernel: CTA barrier at the start of the forward (bit 0) / backward (bit 1) sweep
+  // heis_kernel, time-sliced Adam runs (heis_impl.cuh: launch_heis_sized): the launch covers positions
+  // [ring_start, ring_end) of a ring that walks `ring_visits` times over the B samples; position c is sample c % B on
+  // its visit c / B, i.e. its steps [step0 + visit * nsteps, + nsteps).  Unsliced: ring_start = 0, ring_end = B.
+  long long ring_start, ring_end;
   int colmode;      // engine_kernel<SINGLE>, M_UNITARY: virtual sample b = (sample b / N, column b % N)
   int axp_surface, axp_block;   // heis_kernel: packed rotation axes shared by the surface / block gates
   int last_slot[8];             // heis_kernel: slot of the last fused gate on each qubit

@@ -28,6 +28,8 @@
 // ONE layer of the backward sweep (produced just in time from the forward data), see HEIS_SU2_WORDS below.
 // Per sample and eval for C3 (n = 4, K = 40): ~5.6 k warp instructions (x 1/4 warp) instead of ~22 k.
 #pragma once
+#include <atomic>
+
 #include "engine_impl.cuh"
 
 namespace cpf {
@@ -61,7 +63,7 @@ template <typename R> inline int heis_target_words(int n, int cpt) {
 // program.hpp sat on the critical path of every gate update: a dependent L2 round trip before the load of the
 // packed state).  Constant angles (pidx < 0) stay in the global records.
 struct __align__(8) HSu2 { int16_t pidx[3]; uint16_t axes; };                   // axes: 4 bits per rotation, 15 = unused
-struct __align__(8) HCp { int16_t pidx; uint16_t flags; int16_t prev_lo, prev_hi; };   // flags: 1 penalised, 2 CZ
+struct __align__(8) HCp { int16_t pidx; uint16_t flags; int16_t prev_lo, prev_hi; };   // flags: 1 penalised, 2 CZ, bits [4,7) lower qubit, [8,11) higher qubit
 __host__ __device__ inline int heis_meta_bytes(int n_su2, int n_cp) { return (8 * (n_su2 + n_cp) + 15) & ~15; }
 
 template <typename R, int NQ, int CPT>
@@ -144,25 +146,28 @@ struct HeisSweep {
       tail_fwd<Q + 1>(p, yr, yi, coef);
     }
   }
+  // one block on amplitude bits PA (lower qubit) / PC (higher qubit); cl: slot of the lower-qubit gate
+  template <int PA, int PC>
+  static __device__ __forceinline__ void block_fwd(const R* cl, V (&yr)[N], V (&yi)[N]) {
+    const R* ch = cl + SW;
+    R ar, ai, br, bi;
+    Vec4Load<R>::ld(cl + 4, ar, ai, br, bi);
+    CO::template phase_mask<(1 << PA), (1 << PC)>(yr, yi, ar, ai);
+    CO::template phase_mask<(1 << PC), (1 << PA)>(yr, yi, br, bi);
+    CO::template phase_mask<(1 << PA) | (1 << PC), 0>(yr, yi, ch[4], ch[5]);
+    ry_fwd<PA>(yr, yi, cl);
+    ry_fwd<PC>(yr, yi, ch);
+  }
   template <int J>
   static __device__ __forceinline__ void blocks_fwd(int k0, int K, const R* cs, V (&yr)[N], V (&yi)[N]) {
     if constexpr (J < NBL) {
       if (k0 + J >= K) return;
-      constexpr int PA = NQ - 1 - lo_q(J), PC = NQ - 1 - hi_q(J);
-      const R* cl = cs + 2 * SW * J;
-      const R* ch = cl + SW;
-      R ar, ai, br, bi;
-      Vec4Load<R>::ld(cl + 4, ar, ai, br, bi);
-      CO::template phase_mask<(1 << PA), (1 << PC)>(yr, yi, ar, ai);
-      CO::template phase_mask<(1 << PC), (1 << PA)>(yr, yi, br, bi);
-      CO::template phase_mask<(1 << PA) | (1 << PC), 0>(yr, yi, ch[4], ch[5]);
-      ry_fwd<PA>(yr, yi, cl);
-      ry_fwd<PC>(yr, yi, ch);
+      block_fwd<NQ - 1 - lo_q(J), NQ - 1 - hi_q(J)>(cs + 2 * SW * J, yr, yi);
       blocks_fwd<J + 1>(k0, K, cs, yr, yi);
     }
   }
-  static __device__ __forceinline__ void forward(const KParams<R>& p, const LayerBar lb, const R* coef, V (&yr)[N],
-                                                 V (&yi)[N]) {
+  static __device__ __forceinline__ void forward(const KParams<R>& p, const LayerBar lb, const HCp*, const R* coef,
+                                                 V (&yr)[N], V (&yi)[N]) {
     surface_fwd<0>(yr, yi, coef);
     const int K = p.n_cp;
     const R* cs = coef + SW * NQ;
@@ -345,15 +350,19 @@ struct HeisSweep {
     else v = x;
   }
 
+  // one block of the backward sweep; st: staged rows of the block's two gates (lower, higher), cl: slot of the
+  // lower-qubit gate, cph: the entangler's words
+  template <int PA, int PC>
+  static __device__ __forceinline__ void block_bwd(V (&h)[N], const R* st, R* cl, R* cph, int m) {
+    su2_bwd<PC>(h, st + STW, cl + SW, m);
+    su2_bwd<PA>(h, st, cl, m);
+    phase_bwd<PA, PC>(h, cph, m);
+  }
   template <int J>
   static __device__ __forceinline__ void blocks_bwd(int k0, int K, R* cs, const R* stage, R* cph, int m, V (&h)[N]) {
     if constexpr (J >= 0) {
-      if (k0 + J < K) {
-        constexpr int PA = NQ - 1 - lo_q(J), PC = NQ - 1 - hi_q(J);
-        su2_bwd<PC>(h, stage + STW * (2 * J + 1), cs + 2 * SW * J + SW, m);
-        su2_bwd<PA>(h, stage + STW * (2 * J), cs + 2 * SW * J, m);
-        phase_bwd<PA, PC>(h, cph + CW * J, m);
-      }
+      if (k0 + J < K)
+        block_bwd<NQ - 1 - lo_q(J), NQ - 1 - hi_q(J)>(h, stage + STW * (2 * J), cs + 2 * SW * J, cph + CW * J, m);
       blocks_bwd<J - 1>(k0, K, cs, stage, cph, m, h);
     }
   }
@@ -373,8 +382,9 @@ struct HeisSweep {
   }
   // Staging of one layer (blocks k0 .. k0 + NBL - 1): the sample's lanes split the layer's 2 NBL fused gates.
   // e^{i zeta} = d e^{i a/2}, d = A (lower-qubit gate) / B (higher-qubit gate) of the forward sweep's merged diagonal.
-  static __device__ __forceinline__ void stage_layer(int k0, int K, const R* coef, const R* cph0, R* stage, int m) {
-    const int nb = K - k0 < NBL ? K - k0 : NBL;
+  static __device__ __forceinline__ void stage_layer(int k0, int K, const R* coef, const R* cph0, R* stage, int m,
+                                                     int group = NBL) {
+    const int nb = K - k0 < group ? K - k0 : group;
 #pragma unroll 1
     for (int j = m; j < 2 * nb; j += TPS) {
       const int k = k0 + (j >> 1), hi = j & 1;
@@ -402,8 +412,8 @@ struct HeisSweep {
       tail_bwd<Q + 1>(p, coef, m, h);
     }
   }
-  static __device__ __forceinline__ void backward(const KParams<R>& p, const LayerBar lb, R* coef, R* stage, R* cph0,
-                                                  int m, V (&h)[N]) {
+  static __device__ __forceinline__ void backward(const KParams<R>& p, const LayerBar lb, const HCp*, R* coef, R* stage,
+                                                  R* cph0, int m, V (&h)[N]) {
     const int K = p.n_cp;
     if (lb.bwd) __syncthreads();
     tail_bwd<0>(p, coef, m, h);
@@ -417,6 +427,76 @@ struct HeisSweep {
     stage_surface(coef, stage, m);
     __syncwarp();
     surface_bwd<NQ - 1>(coef, stage, m, h);
+  }
+};
+
+// The same sweeps for ANY block-structured template (topology.py:7-20 allows every `layer`; the paper's kite and
+// square Toffoli-4 layers, twisted placements, non-periodic free blocks): the qubit pair of a block is read from the
+// shared-memory gate metadata and dispatched by one uniform switch per block into the compile-time-pair code above
+// (n (n - 1) / 2 variants).  All warps of a CTA take the same case, so the instruction-cache footprint per layer is
+// what the compile-time-layer kernels have; the cost is the branch and the lost scheduling across block boundaries.
+#define CPF_PAIR_LIST(X) X(0, 1) X(0, 2) X(0, 3) X(0, 4) X(1, 2) X(1, 3) X(1, 4) X(2, 3) X(2, 4) X(3, 4)
+template <typename R, int NQ, int CPT>
+struct HeisSweepAny : HeisSweep<R, NQ, CPT, 1, 0x0ull, 0x1ull> {
+  using Base = HeisSweep<R, NQ, CPT, 1, 0x0ull, 0x1ull>;
+  using V = typename Base::V;
+  static constexpr int N = Base::N, SW = Base::SW, CW = Base::CW, STW = Base::STW, TPS = Base::TPS;
+  static constexpr int GROUP = 4;                                   // blocks staged at a time (backward sweep)
+  static constexpr int NSTAGE = 2 * GROUP > NQ ? 2 * GROUP : NQ;
+  static __device__ __forceinline__ int pair_code(const HCp& md) { return ((md.flags >> 4) & 7) * 8 + ((md.flags >> 8) & 7); }
+
+  static __device__ __forceinline__ void forward(const KParams<R>& p, const LayerBar lb, const HCp* s_cp, const R* coef,
+                                                 V (&yr)[N], V (&yi)[N]) {
+    Base::template surface_fwd<0>(yr, yi, coef);
+    const int K = p.n_cp;
+    const R* cs = coef + SW * NQ;
+    if (lb.fwd) __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      switch (pair_code(s_cp[k])) {
+#define CPF_X(LO, HI)                                                                                        \
+        case LO * 8 + HI:                                                                                    \
+          if constexpr (HI < NQ) Base::template block_fwd<NQ - 1 - LO, NQ - 1 - HI>(cs, yr, yi);             \
+          break;
+        CPF_PAIR_LIST(CPF_X)
+#undef CPF_X
+        default: break;
+      }
+      cs += 2 * SW;
+    }
+    Base::template tail_fwd<0>(p, yr, yi, coef);
+  }
+
+  static __device__ __forceinline__ void backward(const KParams<R>& p, const LayerBar lb, const HCp* s_cp, R* coef,
+                                                  R* stage, R* cph0, int m, V (&h)[N]) {
+    const int K = p.n_cp;
+    if (lb.bwd) __syncthreads();
+    Base::template tail_bwd<0>(p, coef, m, h);
+#pragma unroll 1
+    for (int k0 = K > 0 ? ((K - 1) / GROUP) * GROUP : -1; k0 >= 0; k0 -= GROUP) {
+      Base::stage_layer(k0, K, coef, cph0, stage, m, GROUP);
+      __syncwarp();
+      const int k1 = k0 + GROUP < K ? k0 + GROUP : K;
+#pragma unroll 1
+      for (int k = k1 - 1; k >= k0; --k) {
+        const R* st = stage + STW * 2 * (k - k0);
+        R* cl = coef + SW * (NQ + 2 * k);
+        R* cph = cph0 + CW * k;
+        switch (pair_code(s_cp[k])) {
+#define CPF_X(LO, HI)                                                                                        \
+          case LO * 8 + HI:                                                                                  \
+            if constexpr (HI < NQ) Base::template block_bwd<NQ - 1 - LO, NQ - 1 - HI>(h, st, cl, cph, m);    \
+            break;
+          CPF_PAIR_LIST(CPF_X)
+#undef CPF_X
+          default: break;
+        }
+      }
+      __syncwarp();
+    }
+    Base::stage_surface(coef, stage, m);
+    __syncwarp();
+    Base::template surface_bwd<NQ - 1>(coef, stage, m, h);
   }
 };
 
@@ -724,7 +804,8 @@ heis_kernel(const KParams<R> p) {
     const CpMeta* md = p.cp + k;
     HCp hm;
     hm.pidx = (int16_t)md->pidx;
-    hm.flags = (uint16_t)(((p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0) ? 1 : 0) | (md->is_cz ? 2 : 0));
+    hm.flags = (uint16_t)(((p.cp_pen ? p.cp_pen[k] != 0 : md->penalised != 0) ? 1 : 0) | (md->is_cz ? 2 : 0) |
+                          ((md->lo_q & 7) << 4) | ((md->hi_q & 7) << 8));
     hm.prev_lo = md->prev_lo; hm.prev_hi = md->prev_hi;
     s_cp[k] = hm;
   }
@@ -733,11 +814,14 @@ heis_kernel(const KParams<R> p) {
 
   const int sl = tid / TPS;   // sample within the block
   const int m = tid % TPS;    // lane within the sample: column group (forward), x >> PB (backward)
-  const long long b_raw = (long long)blockIdx.x * p.spb + sl;
-  const bool active = sl < p.spb && b_raw < p.B;
-  const long long b = active ? b_raw : p.B - 1;
+  // ring position -> (sample, visit); an unsliced launch has ring_start = 0, ring_end = B (visit 0 for everybody)
+  const long long c_raw = p.ring_start + (long long)blockIdx.x * p.spb + sl;
+  const bool active = sl < p.spb && c_raw < p.ring_end;
+  const long long c_pos = active ? c_raw : p.ring_end - 1;
+  const long long b = c_pos % p.B;
+  const long long step0 = p.step0 + (c_pos / p.B) * (long long)p.nsteps;
   const int P = p.P;
-  // idle sample slots (block size rounded up to whole warps) replay sample B-1 in one spare store
+  // idle sample slots (block size rounded up to whole warps) replay the launch's last sample in one spare store
   R* coef = s_coef + (size_t)(sl < p.spb ? sl : p.spb) * p.coef_stride;
   R* stage = coef + SW * p.n_su2;                          // staged rows of one layer of the backward sweep
   R* coef_cp = stage + HEIS_STAGE_WORDS * SWP::NSTAGE;
@@ -748,7 +832,7 @@ heis_kernel(const KParams<R> p) {
   Pk4<R>* pk = reinterpret_cast<Pk4<R>*>(p.pk) + off;
   {
     // pack this sample's optimiser state (a resumed run, step0 > 0, carries its moments and best parameters)
-    const bool resume = p.mode == M_ADAM && p.step0 > 0;
+    const bool resume = p.mode == M_ADAM && step0 > 0;
     for (int i = m; i < P; i += TPS) {
       Pk4<R> v;
       v.th = p.angles[off + i];
@@ -766,10 +850,10 @@ heis_kernel(const KParams<R> p) {
 
   R best = R(0), best_reg_v = R(0);
   bool improved_prev = false;
-  if (p.mode == M_ADAM && p.step0 > 0) { best = p.best_regloss[b]; best_reg_v = p.best_reg[b]; }
+  if (p.mode == M_ADAM && step0 > 0) { best = p.best_regloss[b]; best_reg_v = p.best_reg[b]; }
 
   for (int it = 0; it <= p.nsteps; ++it) {
-    const long long gi = p.step0 + it;
+    const long long gi = step0 + it;
     const int phase = it == 0 ? PH_COEF : (p.mode == M_ADAM ? PH_ADAM : PH_GRAD);
     // ---------------- parameter phase (a sample's threads split the gates) ----------------
     R reg_part = R(0);
@@ -860,7 +944,7 @@ heis_kernel(const KParams<R> p) {
     V yr[N], yi[N];
 #pragma unroll
     for (int r = 0; r < N; ++r) { yr[r] = tv[2 * r]; yi[r] = tv[2 * r + 1]; }
-    SWP::forward(p, lb, coef, yr, yi);
+    SWP::forward(p, lb, s_cp, coef, yr, yi);
 
     // ---------------- pivot to the Pauli basis ----------------
     SWP::gather_wht(yr, yi);
@@ -916,7 +1000,7 @@ heis_kernel(const KParams<R> p) {
     __syncwarp();
 
     // ---------------- Heisenberg sweep ----------------
-    SWP::backward(p, lb, coef, stage, coef_cp, m, h);
+    SWP::backward(p, lb, s_cp, coef, stage, coef_cp, m, h);
     __syncwarp();
   }
 
@@ -1011,6 +1095,56 @@ inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sa
   return g;
 }
 
+// Time slicing of an Adam run whose batch is not a whole number of full waves ("ring slicing").  Every CTA
+// keeps its samples for all the steps of a launch, so a batch of 1.3 waves either runs as 2 rounds of 2/3-full CTAs
+// (the even spread of heis_geometry) or, sliced, as a ring: the T steps are cut into k chunks of T / k, the B k
+// (sample, chunk) items are laid on a ring in sample-major order, and consecutive launches of `slots` items each walk
+// along it.  All launches but the last run at full residency; stream order guarantees that chunk v + 1 of a sample
+// starts after its chunk v has been written back (the run is resumable by construction: split runs are bit-identical
+// to one run).  Predicted time per step of a launch with s resident samples per SM: a + b s with a / b = 28 samples
+// (measured: 16 -> 42 M, 28 -> 58 M, 43 -> 71 M, 60 -> 79 M evals/s); a launch costs about one more step (state
+// pack / unpack, coefficient pass).
+struct HeisSlicing { int k; long long slots; };
+inline double heis_step_cost(double samples_per_sm) { return 1.0 + samples_per_sm / 28.0; }
+inline HeisSlicing heis_slicing(long long B, int nsteps, size_t fixed_bytes, size_t per_sample, int tps, int maxt, int regs,
+                                int n_sm, bool allowed) {
+  HeisSlicing best{1, 0};
+  const HeisGeometry full = heis_geometry((long long)1 << 40, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
+  const long long slots = (long long)full.spb * full.ctas * n_sm;
+  best.slots = slots;
+  int forced = -1;
+  if (const char* e = getenv("CPF_HEIS_SLICES")) forced = atoi(e);
+  if (!allowed || forced == 0 || forced == 1 || B <= 0 || nsteps < 2) return best;
+  auto cost = [&](int k) {
+    if (k == 1) {
+      const HeisGeometry g = heis_geometry(B, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
+      const long long rounds = (g.grid + (long long)g.ctas * n_sm - 1) / ((long long)g.ctas * n_sm);
+      return (double)rounds * (nsteps + 1) * heis_step_cost((double)g.spb * g.ctas);
+    }
+    const long long items = B * k, fullw = items / slots, rest = items % slots;
+    const int C = nsteps / k;
+    double t = (double)fullw * (C + 1) * heis_step_cost((double)full.spb * full.ctas);
+    if (rest) {
+      const HeisGeometry g = heis_geometry(rest, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
+      const long long rounds = (g.grid + (long long)g.ctas * n_sm - 1) / ((long long)g.ctas * n_sm);
+      t += (double)rounds * (C + 1) * heis_step_cost((double)g.spb * g.ctas);
+    }
+    return t;
+  };
+  if (forced > 1) {
+    if (nsteps % forced == 0) best.k = forced;
+    return best;
+  }
+  if (B <= slots) return best;
+  double tb = cost(1);
+  for (int k = 2; k <= 64 && nsteps / k >= 20; ++k) {
+    if (nsteps % k) continue;
+    const double t = cost(k);
+    if (t < tb * 0.995) { tb = t; best.k = k; }
+  }
+  return best;
+}
+
 template <typename R, int NQ, int CPT, typename SWP>
 int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   using C = HCfg<R, NQ, CPT>;
@@ -1018,36 +1152,58 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   p.coef_stride = heis_coef_stride(p.n_su2, p.n_cp, SWP::NSTAGE);
   if (p.P > 32767) { err = "heis kernel: more than 32767 parameters"; return CPF_ERR_UNSUPPORTED; }
   auto kern = heis_kernel<R, NQ, CPT, SWP>;
-  static int regs = 0;      // per instantiation
+  static std::atomic<int> regs_cached{0};      // per instantiation
+  int regs = regs_cached.load(std::memory_order_relaxed);
   if (regs == 0) {
     cudaFuncAttributes fa;
     regs = cudaFuncGetAttributes(&fa, kern) == cudaSuccess ? fa.numRegs : 128;
+    regs_cached.store(regs, std::memory_order_relaxed);
   }
-  const HeisGeometry g = heis_geometry(p.B, (size_t)p.target_bytes + heis_meta_bytes(p.n_su2, p.n_cp),
-                                       (size_t)p.coef_stride * sizeof(R), C::TPS, C::MAXT, regs);
-  p.spb = g.spb;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const size_t fixed = (size_t)p.target_bytes + heis_meta_bytes(p.n_su2, p.n_cp);
+  const size_t per_sample = (size_t)p.coef_stride * sizeof(R);
   // CTA barrier at the start of the forward (bit 0) / backward (bit 1) sweep; env CPF_HEIS_SYNC overrides (tests)
   p.sync_sweeps = 3;
   if (const char* e = getenv("CPF_HEIS_SYNC")) { int v = atoi(e); if (v >= 0 && v <= 3) p.sync_sweeps = v; }
-  if (g.smem > 227 * 1024) {
-    err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
-    return CPF_ERR_UNSUPPORTED;
+  const bool sliceable = p.mode == M_ADAM && p.hist_params == nullptr && p.hist_regloss == nullptr;
+  const HeisSlicing sl = heis_slicing(p.B, p.nsteps, fixed, per_sample, C::TPS, C::MAXT, regs, n_sm, sliceable);
+  const long long ring_total = p.B * sl.k;
+  p.nsteps /= sl.k;
+  bool attr_set = false;
+  const long long per_launch = sl.k > 1 ? sl.slots : ring_total;      // unsliced: one launch over the whole batch
+  for (long long c0 = 0; c0 < ring_total; c0 += per_launch) {
+    const long long count = ring_total - c0 < per_launch ? ring_total - c0 : per_launch;
+    const HeisGeometry g = heis_geometry(count, fixed, per_sample, C::TPS, C::MAXT, regs, n_sm);
+    p.spb = g.spb;
+    p.ring_start = c0; p.ring_end = c0 + count;
+    if (g.smem > 227 * 1024) {
+      err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
+      return CPF_ERR_UNSUPPORTED;
+    }
+    if (!attr_set) {
+      // every launch of a sliced run needs at most the shared memory of a full-residency launch
+      const HeisGeometry gmax = sl.k > 1 ? heis_geometry(sl.slots, fixed, per_sample, C::TPS, C::MAXT, regs, n_sm) : g;
+      const size_t smem_max = g.smem > gmax.smem ? g.smem : gmax.smem;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+      if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      attr_set = true;
+    }
+    if (g.grid <= 0 || count <= 0) return CPF_OK;
+    if (g.grid > 2147483647LL) { err = "batch too large for one launch"; return CPF_ERR_UNSUPPORTED; }
+    kern<<<(unsigned)g.grid, g.block, g.smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("kernel launch: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
   }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-  if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (g.grid <= 0) return CPF_OK;
-  if (g.grid > 2147483647LL) { err = "batch too large for one launch"; return CPF_ERR_UNSUPPORTED; }
-  kern<<<(unsigned)g.grid, g.block, g.smem, st>>>(p);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { err = std::string("kernel launch: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
   return CPF_OK;
 }
 
 // Returns true and sets `rc` when a Heisenberg kernel compiled for this layered program exists.
 // `dry` only answers the question (used before the target is staged in the heis layout).
 template <typename R> bool launch_heis(const KParams<R>& p, const Program& prog, cudaStream_t st,
-                                       std::string& err, int& rc, bool dry);
+                                       std::string& err, int& rc, bool dry, int* n_stage = nullptr);
 // columns per thread of the heis kernels for (dtype, n): selects the target packing
 template <typename R> int heis_cpt(int n_qubits);
 template <typename R> int launch_pack_target_heis(const R* src, R* dst, int n_qubits, int cpt, cudaStream_t st);

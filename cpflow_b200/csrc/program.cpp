@@ -132,7 +132,6 @@ void detect_layered(Program& p) {
     if (ok) { period = c; break; }
   }
   if (K == 0) period = 1;
-  if (period == 0) return;
   // renumber
   std::vector<Su2Meta> su2(p.su2.size());
   for (size_t s = 0; s < p.su2.size(); ++s) su2[new_slot[s]] = p.su2[s];
@@ -151,6 +150,8 @@ void detect_layered(Program& p) {
   for (int j = 0; j < K; ++j) {
     p.cp[j].prev_lo = (int16_t)p.last_slot[lo[j]];
     p.cp[j].prev_hi = (int16_t)p.last_slot[hi[j]];
+    p.cp[j].lo_q = (int16_t)lo[j];
+    p.cp[j].hi_q = (int16_t)hi[j];
     p.last_slot[lo[j]] = n + 2 * j;
     p.last_slot[hi[j]] = n + 2 * j + 1;
   }

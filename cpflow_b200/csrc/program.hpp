@@ -44,6 +44,7 @@ struct CpMeta {
   // layered programs: slot of the previous fused gate on the block's lower / higher qubit (its outgoing
   // Rz phase is still pending when this block starts: heis_impl.cuh, forward with merged diagonals)
   int16_t prev_lo, prev_hi;
+  int16_t lo_q, hi_q;   // the block's qubit pair, lower / higher qubit (block-structured programs)
   double cangle;
 };
 
@@ -84,8 +85,9 @@ struct Program {
   std::vector<CpMeta> cp;
   std::vector<uint8_t> is_cp_param;  // [P]
   int n_rot = 0, n_phase = 0;
-  // layered-template structure (detect_layered): surface SU2 per qubit, then blocks
-  // [phase(lo,hi), SU2(lo), SU2(hi)] whose qubit pairs repeat with period `period`
+  // block structure (detect_layered): surface SU2 per qubit, then blocks [phase(lo,hi), SU2(lo), SU2(hi)].
+  // `layered`: the program has this structure (Heisenberg kernels, heis_impl.cuh); `period` > 0: the qubit pairs
+  // repeat with that period (compile-time-layer kernels), 0: no period of at most 16 blocks
   bool layered = false;
   int period = 0;
   unsigned long long lo_pack = 0, hi_pack = 0;   // 4 bits per block of the layer

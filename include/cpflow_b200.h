@@ -231,7 +231,9 @@ typedef struct cpf_launch_info {
   int32_t threads_per_sample;
   int32_t max_block_threads;
   int32_t words_per_sample;   /* shared-memory words (of the real type) per sample */
-  int32_t reserved;
+  int32_t time_slices;        /* launches-in-a-ring factor k a 2000-step cpf_adam_run over `batch` would use (1: one
+                                 launch; k > 1: steps cut into k chunks so every launch but the last runs at full
+                                 residency — results are bit-identical either way) */
   int64_t grid;
   int64_t smem_bytes;         /* dynamic shared memory per CTA */
 } cpf_launch_info;

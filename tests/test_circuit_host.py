@@ -136,8 +136,22 @@ def test_options_and_results_objects(tmp_path):
     assert abs(back.loss_function(np.eye(8))) < 1e-15
     with pytest.raises(AssertionError):
         cp.Synthesize(chain_layer(3), target_unitary=np.eye(4))
+    # any callable is accepted as unitary_loss_func, as in the reference (main.py:528-529); non-callables are not
+    from cpflow_b200.engine import TorchLoss
+    assert isinstance(cp.Synthesize(chain_layer(3), unitary_loss_func=lambda u: 0.0).unitary_loss_func, TorchLoss)
     with pytest.raises(TypeError):
-        cp.Synthesize(chain_layer(3), unitary_loss_func=lambda u: 0.0)
+        cp.Synthesize(chain_layer(3), unitary_loss_func=3.0)
+    # plain pickle (no dill) round trip of the picklable constrained callables stored in Decomposition._cp_data
+    import pickle
+    from cpflow_b200.cp_utils import _constrained_funcs, insert_params
+    from cpflow_b200.ansatz import Ansatz
+    from cpflow_b200.topology import fill_layers
+    anz = Ansatz(3, "cp", fill_layers(chain_layer(3), 4))
+    circ, u = _constrained_funcs(anz, np.array([0.0, np.pi], dtype=np.float32), [15, 22])
+    circ2, u2 = pickle.loads(pickle.dumps((circ, u)))
+    free = np.arange(anz.num_angles - 2, dtype=np.float32)
+    assert circ2(free).count_ops() == circ(free).count_ops() and u2.indices == [15, 22]
+    assert np.array_equal(circ2.full(free), insert_params(free, [0.0, np.float32(np.pi)], [15, 22]))
 
 
 def test_seed_chain_and_tpe(trials):

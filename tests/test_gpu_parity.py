@@ -540,3 +540,67 @@ def test_six_seven_qubit_state_preparation(n, layer, K, dt):
         assert np.abs(st.best_regloss.cpu().numpy() - np.array([r["regloss"][1].item() for r in res])).max() < 1e-9
     with pytest.raises(L.CpflowError, match="n <= 5"):
         anz.program.loss_grad(a, Loss("hs", np.eye(N)), pen())
+
+
+def _heis_run(prog, a, V, p_):
+    lo, rg_, gr = prog.loss_grad(a, Loss("hs", V), p_)
+    st = prog.adam_state(a.clone())
+    prog.adam_run(st, Loss("hs", V), p_, 0.1, 9)
+    return lo.clone(), gr.clone(), st.best_regloss.clone(), st.angles.clone(), st.best_params.clone()
+
+
+def test_any_layer_runs_on_the_heisenberg_kernel():
+    """Every block-structured template takes the fast path: the paper's kite and square Toffoli-4
+    layers (paper/results/toff4_kite_xyz, toff4_square_xyz), a 5-qubit star, twisted placements and a non-periodic
+    block sequence run on HeisSweepAny (qubit pairs dispatched at run time) and agree with the interpreter kernel;
+    on the standard layers the run-time-pair kernel (CPF_HEIS_ANY=1) reproduces the compile-time-layer kernel."""
+    rng = np.random.default_rng(0)
+    irregular = [[int(a), int(b)] for a, b in (rng.permutation(4)[:2] for _ in range(23))]      # no period <= 16
+    cases = [(4, KITE4, 25, "xyz"), (4, SQUARE4, 21, "xyz"), (5, [[0, 1], [0, 2], [0, 3], [0, 4]], 13, "xyz"),
+             (4, [[3, 1], [2, 0]], 7, "zyx"), (4, irregular, 23, "xz"), (3, [[2, 0], [1, 0]], 5, "xyz")]
+    for n, layer, K, rg in cases:
+        anz = Ansatz(n, "cp", fill_layers(layer, K), rg)
+        V = unitary_group.rvs(2 ** n, random_state=4)
+        for dt in (torch.float32, torch.float64):
+            if n == 5 and dt == torch.float64:
+                continue
+            assert anz.program.launch_plan(37, dtype=dt)["engine"] == 1, (layer, dt)
+            a = torch.tensor(np.random.default_rng(K).uniform(0, 6.28, (37, anz.num_angles)), dtype=dt, device=DEV)
+            ref = _with_env({"CPF_NO_LAYERED": "1"}, lambda: _heis_run(anz.program, a, V, pen()))
+            heis = _heis_run(anz.program, a, V, pen())
+            _assert_same_run(heis, ref, dt, (n, layer, K, rg, dt))
+    for n, layer, K, rg in [(4, chain_layer(4), 40, "xyz"), (3, connected_layer(3), 7, "xyz"), (2, [[0, 1]], 4, "xyz"),
+                            (5, chain_layer(5), 9, "xyz")]:
+        anz = Ansatz(n, "cp", fill_layers(layer, K), rg)
+        V = unitary_group.rvs(2 ** n, random_state=4)
+        a = anz.program.initial_angles(1, 37)
+        fixed = _heis_run(anz.program, a, V, pen())
+        anyk = _with_env({"CPF_HEIS_ANY": "1"}, lambda: _heis_run(anz.program, a, V, pen()))
+        # same arithmetic in the same order per block: identical bits
+        for x, y in zip(fixed, anyk):
+            assert torch.equal(x, y), (n, layer)
+
+
+def test_time_sliced_runs_are_bit_identical():
+    """Batches that are not a whole number of full waves run as a ring of launches over (sample, step-chunk) items
+    (heis_impl.cuh: heis_slicing); a sliced run gives the bits of the single launch, with and without a freeze mask."""
+    anz = Ansatz(4, "cp", fill_layers(chain_layer(4), 12))
+    V = unitary_group.rvs(16, random_state=1)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    plan = anz.program.launch_plan(10 ** 9, n_sm=n_sm)
+    slots = plan["samples_per_cta"] * plan["ctas_per_sm"] * n_sm
+    B = slots + slots // 3 + 5
+    a = anz.program.initial_angles(2, B)
+    fm = (torch.rand(B, anz.num_angles, device=DEV) < 0.1).to(torch.uint8)
+
+    def run(freeze):
+        st = anz.program.adam_state(a.clone(), freeze=freeze)
+        anz.program.adam_run(st, Loss("hs", V), pen() if freeze is None else None, 0.1, 60)
+        anz.program.adam_run(st, Loss("hs", V), pen() if freeze is None else None, 0.1, 40)   # resumed, sliced again
+        return st
+    for freeze in (None, fm):
+        ref = _with_env({"CPF_HEIS_SLICES": "1"}, lambda: run(freeze))
+        for k in ("0", "2", "3", "20"):
+            st = _with_env({"CPF_HEIS_SLICES": k} if k != "0" else {}, lambda: run(freeze))
+            for name in ("angles", "m", "v", "best_params", "best_regloss", "best_reg", "init_regloss", "init_reg"):
+                assert torch.equal(getattr(st, name), getattr(ref, name)), (k, name, freeze is not None)
