@@ -73,6 +73,7 @@ EXPORTS = {
     "cpf_initial_angles": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int32, C.c_void_p, C.c_void_p]),
     "cpf_eval_cost": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cpf_executed_cost": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "cpf_launch_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
@@ -82,7 +83,7 @@ class CpfLaunchInfo(C.Structure):
     """cpf_launch_info (include/cpflow_b200.h)."""
     _fields_ = [("engine", C.c_int32), ("ctas_per_sm", C.c_int32), ("block_threads", C.c_int32),
                 ("samples_per_cta", C.c_int32), ("threads_per_sample", C.c_int32), ("max_block_threads", C.c_int32),
-                ("words_per_sample", C.c_int32), ("time_slices", C.c_int32), ("grid", C.c_int64), ("smem_bytes", C.c_int64)]
+                ("words_per_sample", C.c_int32), ("time_slices", C.c_int32), ("grid", C.c_int64), ("smem_bytes", C.c_int64), ("launches_per_run", C.c_int64)]
 
 
 _lib = None

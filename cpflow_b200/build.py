@@ -67,10 +67,12 @@ def build(force=False, verbose=False, extra_flags=()):
         for _, log in results:
             sys.stderr.write(log)
     if force or _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        tmp = LIB + f".tmp{os.getpid()}"     # link aside and rename: a reader never sees a half-written library
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

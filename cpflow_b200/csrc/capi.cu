@@ -600,9 +600,11 @@ static int launch_plan_t(const cpf::Program* prog, const cpf_loss_spec_kind_only
   out->smem_bytes = (int64_t)g.smem; out->threads_per_sample = tps; out->max_block_threads = maxt;
   out->words_per_sample = stride;
   // time slices an Adam run of `adam_steps` iterations over this batch would be cut into (1 = one launch)
-  out->time_slices = cpf::heis_slicing(batch, adam_steps > 0 ? adam_steps : 2000, target + cpf::heis_meta_bytes(n_su2, n_cp),
-                                       (size_t)stride * sizeof(R), tps, maxt, regs > 0 ? regs : 128,
-                                       n_sm > 0 ? n_sm : 148, true).k;
+  const cpf::HeisSlicing sl = cpf::heis_slicing(batch, adam_steps > 0 ? adam_steps : 2000,
+                                                target + cpf::heis_meta_bytes(n_su2, n_cp), (size_t)stride * sizeof(R), tps,
+                                                maxt, regs > 0 ? regs : 128, n_sm > 0 ? n_sm : 148, true);
+  out->time_slices = sl.k;
+  out->launches_per_run = sl.k > 1 ? (batch * sl.k + sl.slots - 1) / sl.slots : 1;
   return CPF_OK;
 }
 
@@ -810,6 +812,32 @@ int cpf_eval_cost(const cpf_program* prog, int32_t loss_kind, int32_t dtype, dou
   const double rs = dtype == CPF_F64 ? 8.0 : 4.0;
   if (flops) *flops = C * N * (16.0 * p->n_rot + 4.0 * p->n_phase + 8.0);
   if (bytes) *bytes = 6.0 * p->n_params * rs + 2.0 * rs;
+  return CPF_OK;
+}
+
+int cpf_executed_cost(const cpf_program* prog, int32_t loss_kind, int32_t dtype, double* flops) {
+  if (!prog || !flops) return fail(CPF_ERR_INVALID, "NULL argument");
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  const double N = (double)(1 << p->n_qubits), n = p->n_qubits, K = (double)p->cp.size(), G = (double)p->su2.size();
+  cpf_loss_spec ls{};
+  ls.kind = loss_kind;
+  const bool heis = dtype == CPF_F64 ? use_heis<double>(p, &ls) : use_heis<float>(p, &ls);
+  if (heis) {
+    // heis_kernel (heis_impl.cuh), FMA = 2 flop, per sample and step:
+    //   forward   block: 3 diagonal phases on N/4 rows (6 flop per complex amplitude) + 2 Ry in lifting form (3 shears on
+    //             re and im): N^2 (4.5 + 12); surface gate: phase on N/2 rows + Ry: 9 N^2; pending phases at the end: 3 N^2
+    //   backward  fused gate: Rx exchange + merged Rz on the N^2 real coefficients: 4.5 N^2; ZZ pair rotations
+    //             (lifting): 3 N^2 per block; outgoing Rz of the last gate per qubit: 3 N^2
+    //   pivot     Walsh-Hadamard transform (re, im) + seed of h: N^2 (2 n + 6)
+    //   update    per fused gate: chain rule, 3 x Adam, 3 x sin/cos, SU(2) products, ZYZ data, staging: ~232;
+    //             per entangler: Adam, sin/cos, penalty, merged diagonal: ~80
+    *flops = N * N * (28.5 * K + 19.5 * n + 2.0 * n + 6.0) + 232.0 * G + 80.0 * K;
+  } else {
+    // state-adjoint kernels: the credited count plus the uncompute of phi (6 flop per amplitude and rotation on
+    // fused gates, 1.5 per phase gate), with fused gates instead of primitive rotations: C N (22 G + 5.5 K + 8)
+    const double C = loss_kind == CPF_LOSS_STATE ? 1.0 : N;
+    *flops = C * N * (22.0 * G + 5.5 * K + 8.0) + 232.0 * G + 80.0 * K;
+  }
   return CPF_OK;
 }
 

@@ -537,9 +537,21 @@ __device__ __forceinline__ void pk_store(Pk4<double>* q, const Pk4<double>& v) {
   reinterpret_cast<double2*>(q)[1] = make_double2(v.nu, v.best);
 }
 
-__device__ __forceinline__ float rsqrt_fast(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+// MUFU approximations (rsqrt: 2^-22.4, rcp: 1 ulp) refined by one Newton step: the unit phases of the ZYZ data are
+// built from these, and a modulus error of 2e-7 per phase accumulates over the ~3 K diagonal factors of a sweep
+// (measured: worst gradient error of 4096 samples on C3 1.46e-5 with the raw approximations; profiles/grad_accuracy_r2.txt).
+__device__ __forceinline__ float rsqrt_fast(float a) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  const float h = 0.5f * a * r;
+  return fmaf(r, fmaf(-h, r, 0.5f), r);          // r (1.5 - 0.5 a r^2)
+}
 __device__ __forceinline__ double rsqrt_fast(double a) { return rsqrt_r(a); }
-__device__ __forceinline__ float rcp_fast(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float rcp_fast(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return fmaf(r, fmaf(-a, r, 1.0f), r);          // r (2 - a r)
+}
 __device__ __forceinline__ double rcp_fast(double a) { return 1.0 / a; }
 static __device__ __noinline__ SinCos<float> sincos_slow_v(float x) { float s, c; sincosf(x, &s, &c); return {s, c}; }
 // sin/cos for the parameter phase, inlined so the three evaluations of a fused gate interleave
@@ -1103,7 +1115,9 @@ inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sa
 // starts after its chunk v has been written back (the run is resumable by construction: split runs are bit-identical
 // to one run).  Predicted time per step of a launch with s resident samples per SM: a + b s with a / b = 28 samples
 // (measured: 16 -> 42 M, 28 -> 58 M, 43 -> 71 M, 60 -> 79 M evals/s); a launch costs about one more step (state
-// pack / unpack, coefficient pass).
+// pack / unpack, coefficient pass) plus the drift between CTAs that
+// a launch boundary exposes, about 3.5 % of its steps (measured: 10^5 samples in 43 launches of 500 steps lose 4 %,
+// 12 500 samples in 33 launches of 80 steps gain 15 % over two 2/3-full rounds).
 struct HeisSlicing { int k; long long slots; };
 inline double heis_step_cost(double samples_per_sm) { return 1.0 + samples_per_sm / 28.0; }
 inline HeisSlicing heis_slicing(long long B, int nsteps, size_t fixed_bytes, size_t per_sample, int tps, int maxt, int regs,
@@ -1119,23 +1133,24 @@ inline HeisSlicing heis_slicing(long long B, int nsteps, size_t fixed_bytes, siz
     if (k == 1) {
       const HeisGeometry g = heis_geometry(B, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
       const long long rounds = (g.grid + (long long)g.ctas * n_sm - 1) / ((long long)g.ctas * n_sm);
-      return (double)rounds * (nsteps + 1) * heis_step_cost((double)g.spb * g.ctas);
+      return (double)rounds * (nsteps + 3) * heis_step_cost((double)g.spb * g.ctas);
     }
     const long long items = B * k, fullw = items / slots, rest = items % slots;
-    const int C = nsteps / k;
-    double t = (double)fullw * (C + 1) * heis_step_cost((double)full.spb * full.ctas);
+    const double C = 1.035 * (nsteps / k) + 3.0;
+    double t = (double)fullw * C * heis_step_cost((double)full.spb * full.ctas);
     if (rest) {
       const HeisGeometry g = heis_geometry(rest, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
       const long long rounds = (g.grid + (long long)g.ctas * n_sm - 1) / ((long long)g.ctas * n_sm);
-      t += (double)rounds * (C + 1) * heis_step_cost((double)g.spb * g.ctas);
+      t += (double)rounds * C * heis_step_cost((double)g.spb * g.ctas);
     }
     return t;
   };
+  // a ring shorter than one launch would put two visits of a sample into the same launch: never sliced
+  if (B <= slots) return best;
   if (forced > 1) {
     if (nsteps % forced == 0) best.k = forced;
     return best;
   }
-  if (B <= slots) return best;
   double tb = cost(1);
   for (int k = 2; k <= 64 && nsteps / k >= 20; ++k) {
     if (nsteps % k) continue;
@@ -1171,7 +1186,7 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
   const HeisSlicing sl = heis_slicing(p.B, p.nsteps, fixed, per_sample, C::TPS, C::MAXT, regs, n_sm, sliceable);
   const long long ring_total = p.B * sl.k;
   p.nsteps /= sl.k;
-  bool attr_set = false;
+  long long smem_attr = 0;      // per call: cudaFuncSetAttribute is cheap, the limit is re-asserted for this device
   const long long per_launch = sl.k > 1 ? sl.slots : ring_total;      // unsliced: one launch over the whole batch
   for (long long c0 = 0; c0 < ring_total; c0 += per_launch) {
     const long long count = ring_total - c0 < per_launch ? ring_total - c0 : per_launch;
@@ -1182,14 +1197,12 @@ int launch_heis_sized(KParams<R> p, cudaStream_t st, std::string& err) {
       err = "program too large for the shared-memory coefficient store (" + std::to_string(g.smem) + " bytes)";
       return CPF_ERR_UNSUPPORTED;
     }
-    if (!attr_set) {
-      // every launch of a sliced run needs at most the shared memory of a full-residency launch
-      const HeisGeometry gmax = sl.k > 1 ? heis_geometry(sl.slots, fixed, per_sample, C::TPS, C::MAXT, regs, n_sm) : g;
-      const size_t smem_max = g.smem > gmax.smem ? g.smem : gmax.smem;
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if ((long long)g.smem > smem_attr) {
+      // the opt-in limit only ever grows (per instantiation and device; a smaller launch runs under a larger limit)
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
       if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return CPF_ERR_CUDA; }
       cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_set = true;
+      smem_attr = (long long)g.smem;
     }
     if (g.grid <= 0 || count <= 0) return CPF_OK;
     if (g.grid > 2147483647LL) { err = "batch too large for one launch"; return CPF_ERR_UNSUPPORTED; }

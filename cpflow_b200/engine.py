@@ -72,6 +72,12 @@ class Program:
         L.check(L.load().cpf_eval_cost(self._h, int(loss_kind), _DT[dtype], C.byref(f), C.byref(b)))
         return f.value, b.value
 
+    def executed_cost(self, loss_kind=L.LOSS_HS, dtype=torch.float32):
+        """Floating-point operations per evaluation the chosen kernel executes (cpf_executed_cost)."""
+        f = C.c_double()
+        L.check(L.load().cpf_executed_cost(self._h, int(loss_kind), _DT[dtype], C.byref(f)))
+        return f.value
+
     def launch_plan(self, batch, loss_kind=L.LOSS_HS, dtype=torch.float32, n_sm=0, regs_per_thread=0):
         """The launch geometry the engine would use for `batch` samples (cpf_launch_plan; needs no device)."""
         info = L.CpfLaunchInfo()

@@ -219,6 +219,12 @@ int cpf_initial_angles(const cpf_program* prog, int32_t dtype, uint64_t seed,
 int cpf_eval_cost(const cpf_program* prog, int32_t loss_kind, int32_t dtype, double* flops,
                   double* bytes);
 
+/* Floating-point operations the engine EXECUTES per loss+grad(+Adam) evaluation of one sample on the kernel it would
+ * pick for (program, loss, dtype), FMA = 2: the Heisenberg-picture kernel needs far fewer than the credited
+ * adjoint-sweep count of cpf_eval_cost (bench.py reports both: roofline.frac is executed flop/s over the measured
+ * FP32 peak).  Derived from the fused schedule; cross-checked against the ncu opcode mix. */
+int cpf_executed_cost(const cpf_program* prog, int32_t loss_kind, int32_t dtype, double* flops);
+
 /* Diagnostics: the launch geometry cpf_adam_run / cpf_loss_grad would use for `batch` samples (no reference
  * counterpart; it makes the geometry rules testable without a device).  engine: 1 = Heisenberg-picture kernel
  * (HS loss on a layered template), 0 = state-adjoint kernel (the remaining fields are 0).  n_sm / regs_per_thread:
@@ -236,6 +242,7 @@ typedef struct cpf_launch_info {
                                  residency — results are bit-identical either way) */
   int64_t grid;
   int64_t smem_bytes;         /* dynamic shared memory per CTA */
+  int64_t launches_per_run;   /* engine-kernel launches of that cpf_adam_run (1 unless time-sliced) */
 } cpf_launch_info;
 int cpf_launch_plan(const cpf_program* prog, int32_t loss_kind, int32_t dtype, int64_t batch, int32_t n_sm,
                     int32_t regs_per_thread, cpf_launch_info* out);

@@ -130,7 +130,7 @@ def test_static_ccz_readme_example(tmp_path):
         from cpflow_b200.circuit import gates_depth
         assert d.cz_depth == gates_depth(["cz"], d.circuit)
         assert hst(d.circuit.unitary(), d.unitary) < 1e-12
-        assert abs(d.loss - Loss("hs", CCZ)(d.circuit.unitary())) < 1e-12
+        assert abs(d.loss - Loss("hs", CCZ)(d.circuit.unitary())) < 1e-9      # 1 - |t|^2 / 64 cancels to ~1e-7
         u_func, circ_func, free = d._cp_data
         assert hst(u_func(free).astype(complex), d.unitary) < 1e-5 and circ_func(free).count_ops()["cp"] == 12
     import pickle
@@ -189,3 +189,25 @@ def test_static_toffoli3_finds_known_optimum():
     assert 0.12 < len(counts) / 400 < 0.45
     d = res.decompositions[0]
     assert hst(d.unitary, u_toff3) < 1e-5
+
+
+# Best known CZ counts of the 4-qubit Toffoli per topology (paper/CPFlow.tex:480) at hyper-parameter points the
+# reference's own stored trials found productive (tests/golden/trials.json); profiles/toff4_best_r2.txt keeps a full run.
+@pytest.mark.parametrize("name,layer,K,r,best,B", [
+    ("star", [[0, 1], [0, 2], [0, 3]], 26, 0.000793, 16, 20000),
+    ("chain", chain_layer(4), 26, 0.000256, 18, 60000),
+    ("kite", [[0, 1], [1, 2], [2, 3], [1, 3]], 25, 0.000648, 14, 20000),
+    ("square", [[0, 1], [1, 2], [2, 3], [3, 0]], 24, 0.000528, 16, 20000),
+    ("connected", connected_layer(4), 23, 0.000528, 14, 20000)])
+def test_static_toffoli4_reaches_best_known_counts(name, layer, K, r, best, B):
+    """Full Synthesize.static() runs reproduce the reference's minimal CZ counts on the benchmark target of the
+    headline metric (north_star: 'identical best CZ counts'): 16 (star) / 18 (chain) / 14 (kite) / 16 (square) /
+    14 (connected).  Kite and square run on the run-time-pair Heisenberg kernel."""
+    syn = cp.Synthesize(layer, target_unitary=u_toff4, label=f"toff4_{name}")
+    opts = cp.StaticOptions(num_cp_gates=K, r=r, accepted_num_cz_gates=best, num_samples=B)
+    res = syn.static(opts, save_results=False)
+    counts = sorted(d.cz_count for d in res.decompositions)
+    assert counts and counts[0] <= best, (name, counts[:5], len(syn.last_prospective_cz_counts))
+    assert counts[0] >= best - 1          # a count below the best known one would be news: look at it before trusting it
+    for d in res.decompositions:
+        assert hst(d.unitary, u_toff4) < 1e-5 and d.cz_count == d.circuit.count_ops()["cz"]

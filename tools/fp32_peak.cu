@@ -77,6 +77,7 @@ int main(int argc, char** argv) {
     for (int bps = 4; bps <= 8; bps *= 2) {
       run<0>("ffma_flops", ILP * 2.0, 4000, bps);
       run<1>("ffma2_flops", ILP * 4.0, 4000, bps);
+      run<3>("dfma_flops", ILP / 2 * 2.0, 1000, bps);      // FP64 FMA peak: roofline denominator of the complex128 kernels
     }
     return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1;
   }

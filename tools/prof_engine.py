@@ -25,7 +25,8 @@ ap.add_argument("--loss", default="hs")
 a = ap.parse_args()
 
 n = a.n
-layer = {"chain": chain_layer(n), "connected": connected_layer(n), "star": [[0, q] for q in range(1, n)]}[a.layer]
+layer = {"chain": chain_layer(n), "connected": connected_layer(n), "star": [[0, q] for q in range(1, n)],
+         "kite": [[0, 1], [1, 2], [2, 3], [1, 3]], "square": [[0, 1], [1, 2], [2, 3], [3, 0]]}[a.layer]
 anz = Ansatz(n, "cp", fill_layers(layer, a.K))
 prog = anz.program
 N = 1 << n
