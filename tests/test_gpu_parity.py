@@ -56,12 +56,16 @@ def test_adam_loop_parity_c3_shape(layer_name, layer, freeze):
         assert m["frozen_moved"] == 0.0
 
 
-def test_adam_loop_parity_c3_shape_f32():
-    """Same kernel in complex64 (the PLAIN instantiation of the bench) over a short horizon: trajectories are
-    chaotic in float32, so the loop is pinned over 10 iterations."""
-    m = measure_adam_loop(4, chain_layer(4), 40, u_toff4, B=32, T=10, dt=torch.float32)
+@pytest.mark.parametrize("T,tol", [(1, 5e-7), (3, 1e-4)])
+def test_adam_loop_parity_c3_shape_f32(T, tol):
+    """Same kernel in complex64 (the PLAIN instantiation the bench times) against the float32 oracle loop.  Adam's
+    first steps move every parameter by ~lr whatever the size of its gradient (update = lr g / (|g| + eps) at step 1),
+    so float32 trajectories separate quickly (measured on this case, profiles/grad_accuracy_r2.txt: best-regloss error
+    9e-8 after 1 step, 3e-5 after 3, 1e-3 after 6); the complex64 loop is therefore pinned over 1 and 3 iterations
+    and the long horizon in complex128 above."""
+    m = measure_adam_loop(4, chain_layer(4), 40, u_toff4, B=32, T=T, dt=torch.float32)
     assert m["engine"] == 1
-    assert m["init_regloss"] < 2e-6 and m["best_regloss"] < 2e-4 and m["best_reg"] < 2e-4, m
+    assert m["init_regloss"] < 5e-7 and m["best_regloss"] < tol and m["best_reg"] < tol, m
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
