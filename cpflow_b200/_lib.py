@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcpflow_b200.so")
+# CPF_LIB_PATH: load another build of the same library (A/B measurements of kernel variants, tools/)
+LIB_PATH = os.environ.get("CPF_LIB_PATH") or os.path.join(HERE, "lib", "libcpflow_b200.so")
 
 MAX_SEGMENTS = 16
 MAX_QUBITS = 7
@@ -48,7 +49,8 @@ class CpfAdamBuffers(C.Structure):
     _fields_ = [("angles", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("freeze", C.c_void_p),
                 ("best_params", C.c_void_p), ("best_regloss", C.c_void_p), ("best_reg", C.c_void_p),
                 ("init_regloss", C.c_void_p), ("init_reg", C.c_void_p), ("hist_params", C.c_void_p),
-                ("hist_regloss", C.c_void_p), ("hist_len", C.c_int64)]
+                ("hist_regloss", C.c_void_p), ("hist_len", C.c_int64), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_int64)]
 
 
 EXPORTS = {
@@ -65,6 +67,7 @@ EXPORTS = {
     "cpf_adam_run": (C.c_int, [C.c_void_p, C.POINTER(CpfLossSpec), C.POINTER(CpfPenaltySpec),
                                C.POINTER(CpfAdamSpec), C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                C.POINTER(CpfAdamBuffers), C.c_void_p]),
+    "cpf_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int64)]),
     "cpf_adam_step": (C.c_int, [C.c_void_p, C.POINTER(CpfPenaltySpec), C.POINTER(CpfAdamSpec), C.c_int32, C.c_int64,
                                 C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(CpfAdamBuffers), C.c_void_p]),
     "cpf_count_cz": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_double, C.c_void_p,

@@ -30,6 +30,34 @@ int cuda_fail(const char* what, cudaError_t e) {
     if (e__ != cudaSuccess) return cuda_fail(#call, e__);     \
   } while (0)
 
+// Per-call scratch (packed optimiser state, staged target, penalty mask): carved from a caller-provided workspace
+// (cpf_adam_buffers.workspace, sized by cpf_workspace_bytes) or, without one, taken from the device's stream-ordered
+// pool and returned to it when the call has been enqueued.
+struct Scratch {
+  char* base = nullptr;
+  size_t size = 0, used = 0;
+  cudaStream_t st = nullptr;
+  void* owned[8] = {nullptr};
+  int n_owned = 0;
+  static size_t align(size_t b) { return (b + 255) & ~(size_t)255; }
+  int get(void** out, size_t bytes) {
+    bytes = align(bytes ? bytes : 1);
+    if (base) {
+      if (used + bytes > size)
+        return fail(CPF_ERR_INVALID, "workspace too small: cpf_workspace_bytes gives the size this call needs");
+      *out = base + used;
+      used += bytes;
+      return CPF_OK;
+    }
+    if (n_owned >= 8) return fail(CPF_ERR_NOMEM, "scratch table full");
+    cudaError_t e = cudaMallocAsync(out, bytes, st);
+    if (e != cudaSuccess) return cuda_fail("cudaMallocAsync(scratch)", e);
+    owned[n_owned++] = *out;
+    return CPF_OK;
+  }
+  ~Scratch() { for (int i = 0; i < n_owned; ++i) cudaFreeAsync(owned[i], st); }
+};
+
 // per-device copy of the schedule and gate metadata, created on first use
 int device_program(const cpf::Program* prog, cpf::DeviceProgram* out) {
   int dev = 0;
@@ -109,9 +137,8 @@ int launch_any(const cpf::KParams<R>& p, const cpf::Program* prog, bool single, 
 }
 
 template <typename R>
-int fill_penalty(const cpf::Program* prog, const cpf_penalty_spec* pen, cpf::KParams<R>& p,
-                 uint8_t** cp_pen_dev, cudaStream_t st) {
-  *cp_pen_dev = nullptr;
+int fill_penalty(const cpf::Program* prog, const cpf_penalty_spec* pen, cpf::KParams<R>& p, Scratch& sc) {
+  cudaStream_t st = sc.st;
   if (!pen || pen->kind == CPF_PEN_NONE) return CPF_OK;
   if (pen->kind != CPF_PEN_PIECEWISE && pen->kind != CPF_PEN_L1)
     return fail(CPF_ERR_INVALID, "unknown penalty kind");
@@ -134,26 +161,30 @@ int fill_penalty(const cpf::Program* prog, const cpf_penalty_spec* pen, cpf::KPa
     for (size_t k = 0; k < prog->cp.size(); ++k)
       flags[k] = prog->cp[k].pidx >= 0 && pen->cp_mask[prog->cp[k].pidx] ? 1 : 0;
     if (!flags.empty()) {
-      CPF_CUDA(cudaMallocAsync((void**)cp_pen_dev, flags.size(), st));
+      uint8_t* dev = nullptr;
+      int rc = sc.get((void**)&dev, flags.size());
+      if (rc) return rc;
       // pageable source: the runtime stages the bytes before returning, so `flags` may die
-      CPF_CUDA(cudaMemcpyAsync(*cp_pen_dev, flags.data(), flags.size(), cudaMemcpyHostToDevice, st));
-      p.cp_pen = *cp_pen_dev;
+      CPF_CUDA(cudaMemcpyAsync(dev, flags.data(), flags.size(), cudaMemcpyHostToDevice, st));
+      p.cp_pen = dev;
     }
   }
   return CPF_OK;
 }
 
 template <typename R>
-int stage_target(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams<R>& p, bool single,
-                 R** packed, cudaStream_t st) {
+int stage_target(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams<R>& p, bool single, Scratch& sc) {
+  cudaStream_t st = sc.st;
   const int cpt = single ? 1 : cpf::cpt_for<R>(prog->n_qubits);
   const int words = cpf::target_words<R>(prog->n_qubits, cpt, single);
   const size_t bytes = ((size_t)words * sizeof(R) + 15) & ~(size_t)15;
-  CPF_CUDA(cudaMallocAsync((void**)packed, bytes, st));
-  if (bytes != (size_t)words * sizeof(R)) CPF_CUDA(cudaMemsetAsync(*packed, 0, bytes, st));
-  int rc = cpf::launch_pack_target<R>((const R*)loss->target, *packed, prog->n_qubits, cpt, single, st);
+  R* packed = nullptr;
+  int rc = sc.get((void**)&packed, bytes);
+  if (rc) return rc;
+  if (bytes != (size_t)words * sizeof(R)) CPF_CUDA(cudaMemsetAsync(packed, 0, bytes, st));
+  rc = cpf::launch_pack_target<R>((const R*)loss->target, packed, prog->n_qubits, cpt, single, st);
   if (rc) return fail(rc, "pack_target launch failed");
-  p.target_packed = *packed;
+  p.target_packed = packed;
   p.target_bytes = (int)bytes;
   p.loss_kind = loss->kind;
   return CPF_OK;
@@ -196,22 +227,35 @@ bool use_heis(const cpf::Program* prog, const cpf_loss_spec* loss) {
   return cpf::launch_heis<R>(dummy, *prog, nullptr, err, rc, true);
 }
 
+// bytes of the two heis scratch blocks: staged target; per-gate scratch followed by the packed optimiser state
 template <typename R>
-int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams<R>& p, R** packed, R** aux,
-               cudaStream_t st) {
-  keep_pool_memory();
+void heis_scratch_sizes(const cpf::Program* prog, int64_t batch, size_t* target_bytes, size_t* aux_pad, size_t* pk_bytes) {
   const int cpt = cpf::heis_cpt<R>(prog->n_qubits);
   const int words = cpf::heis_target_words<R>(prog->n_qubits, cpt);
-  const size_t bytes = ((size_t)words * sizeof(R) + 15) & ~(size_t)15;
-  CPF_CUDA(cudaMallocAsync((void**)packed, bytes, st));
+  *target_bytes = ((size_t)words * sizeof(R) + 15) & ~(size_t)15;
+  const size_t aux_bytes = (size_t)batch * (prog->su2.empty() ? 1 : prog->su2.size()) * 4 * sizeof(R);
+  *aux_pad = (aux_bytes + 31) & ~(size_t)31;
+  *pk_bytes = (size_t)batch * (prog->n_params > 0 ? prog->n_params : 1) * 4 * sizeof(R);
+}
+
+template <typename R>
+int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams<R>& p, Scratch& sc) {
+  cudaStream_t st = sc.st;
+  if (!sc.base) keep_pool_memory();
+  const int cpt = cpf::heis_cpt<R>(prog->n_qubits);
+  const int words = cpf::heis_target_words<R>(prog->n_qubits, cpt);
+  size_t bytes, aux_pad, pk_bytes;
+  heis_scratch_sizes<R>(prog, p.B, &bytes, &aux_pad, &pk_bytes);
+  R* packed_v = nullptr; R* aux_v = nullptr;
+  R** packed = &packed_v; R** aux = &aux_v;
+  int rc = sc.get((void**)packed, bytes);
+  if (rc) return rc;
   if (bytes != (size_t)words * sizeof(R)) CPF_CUDA(cudaMemsetAsync(*packed, 0, bytes, st));
-  int rc = cpf::launch_pack_target_heis<R>((const R*)loss->target, *packed, prog->n_qubits, cpt, st);
+  rc = cpf::launch_pack_target_heis<R>((const R*)loss->target, *packed, prog->n_qubits, cpt, st);
   if (rc) return fail(rc, "pack_target_heis launch failed");
-  const size_t aux_bytes = (size_t)p.B * (prog->su2.empty() ? 1 : prog->su2.size()) * 4 * sizeof(R);
-  // one allocation: per-gate scratch, then the packed optimiser state (32-byte aligned)
-  const size_t aux_pad = (aux_bytes + 31) & ~(size_t)31;
-  const size_t pk_bytes = (size_t)p.B * (prog->n_params > 0 ? prog->n_params : 1) * 4 * sizeof(R);
-  CPF_CUDA(cudaMallocAsync((void**)aux, aux_pad + pk_bytes, st));
+  // one block: per-gate scratch, then the packed optimiser state (32-byte aligned)
+  rc = sc.get((void**)aux, aux_pad + pk_bytes);
+  if (rc) return rc;
   p.pk = reinterpret_cast<char*>(*aux) + aux_pad;
   p.target_packed = *packed;
   p.target_bytes = (int)bytes;
@@ -267,10 +311,11 @@ int run_loss_grad(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf
   if (rc) return rc;
   p.mode = cpf::M_LOSSGRAD;
   p.angles = (R*)angles; p.loss_out = (R*)loss_out; p.reg_out = (R*)reg_out; p.grad_out = (R*)grad_out;
-  uint8_t* cp_pen = nullptr; R* packed = nullptr; R* aux = nullptr;
+  Scratch sc;
+  sc.st = st;
   const bool heis = use_heis<R>(prog, loss) && (unsigned long long)batch * (unsigned long long)prog->n_params < (1ull << 32);
-  rc = fill_penalty(prog, pen, p, &cp_pen, st);
-  if (!rc) rc = heis ? stage_heis(prog, loss, p, &packed, &aux, st) : stage_target(prog, loss, p, single, &packed, st);
+  rc = fill_penalty(prog, pen, p, sc);
+  if (!rc) rc = heis ? stage_heis(prog, loss, p, sc) : stage_target(prog, loss, p, single, sc);
   if (!rc && grad_out) {
     cudaError_t e = cudaMemsetAsync(grad_out, 0, (size_t)batch * prog->n_params * sizeof(R), st);
     if (e != cudaSuccess) rc = cuda_fail("cudaMemsetAsync(grad)", e);
@@ -281,9 +326,6 @@ int run_loss_grad(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf
     else rc = launch_any<R>(p, prog, single, st, err);
     if (rc) fail(rc, err);
   }
-  if (packed) cudaFreeAsync(packed, st);
-  if (aux) cudaFreeAsync(aux, st);
-  if (cp_pen) cudaFreeAsync(cp_pen, st);
   return rc;
 }
 
@@ -317,20 +359,42 @@ int run_adam(const cpf::Program* prog, const cpf_loss_spec* loss, const cpf_pena
   p.best_params = (R*)buf->best_params; p.best_regloss = (R*)buf->best_regloss;
   p.best_reg = (R*)buf->best_reg; p.init_regloss = (R*)buf->init_regloss; p.init_reg = (R*)buf->init_reg;
   p.hist_params = (R*)buf->hist_params; p.hist_regloss = (R*)buf->hist_regloss; p.hist_len = buf->hist_len;
-  uint8_t* cp_pen = nullptr; R* packed = nullptr; R* aux = nullptr;
+  Scratch sc;
+  sc.st = st;
+  if (buf->workspace) {
+    if (((uintptr_t)buf->workspace & 255) != 0) return fail(CPF_ERR_INVALID, "workspace must be 256-byte aligned");
+    sc.base = (char*)buf->workspace;
+    sc.size = buf->workspace_bytes > 0 ? (size_t)buf->workspace_bytes : 0;
+  }
   const bool heis = use_heis<R>(prog, loss) && (unsigned long long)batch * (unsigned long long)prog->n_params < (1ull << 32);
-  rc = fill_penalty(prog, pen, p, &cp_pen, st);
-  if (!rc) rc = heis ? stage_heis(prog, loss, p, &packed, &aux, st) : stage_target(prog, loss, p, single, &packed, st);
+  rc = fill_penalty(prog, pen, p, sc);
+  if (!rc) rc = heis ? stage_heis(prog, loss, p, sc) : stage_target(prog, loss, p, single, sc);
   std::string err;
   if (!rc) {
     if (heis) cpf::launch_heis<R>(p, *prog, st, err, rc, false);
     else rc = launch_any<R>(p, prog, single, st, err);
     if (rc) fail(rc, err);
   }
-  if (packed) cudaFreeAsync(packed, st);
-  if (aux) cudaFreeAsync(aux, st);
-  if (cp_pen) cudaFreeAsync(cp_pen, st);
   return rc;
+}
+
+// bytes of scratch one cpf_adam_run / cpf_loss_grad needs (the blocks Scratch::get hands out, each 256-byte aligned)
+template <typename R>
+int64_t workspace_bytes_t(const cpf::Program* prog, int32_t loss_kind, int64_t batch) {
+  cpf_loss_spec ls{};
+  ls.kind = loss_kind;
+  const bool single = loss_kind == CPF_LOSS_STATE;
+  const bool heis = use_heis<R>(prog, &ls) && (unsigned long long)batch * (unsigned long long)prog->n_params < (1ull << 32);
+  size_t total = Scratch::align(prog->cp.empty() ? 1 : prog->cp.size());          // penalty mask
+  if (heis) {
+    size_t tb, ap, pk;
+    heis_scratch_sizes<R>(prog, batch, &tb, &ap, &pk);
+    total += Scratch::align(tb) + Scratch::align(ap + pk);
+  } else {
+    const int cpt = single ? 1 : cpf::cpt_for<R>(prog->n_qubits);
+    total += Scratch::align((((size_t)cpf::target_words<R>(prog->n_qubits, cpt, single) * sizeof(R)) + 15) & ~(size_t)15);
+  }
+  return (int64_t)total;
 }
 
 // ---- count_cz / projection (cp_utils.py:45-77, 111-141) ----
@@ -547,10 +611,13 @@ static int run_adam_step(const cpf::Program* prog, const cpf_penalty_spec* pen, 
                          int64_t step, const void* loss, const void* grad, const cpf_adam_buffers* buf, cudaStream_t st) {
   cpf::KParams<R> p;
   std::memset(&p, 0, sizeof(p));
-  uint8_t* unused = nullptr;
   // fill_penalty validates the spec and converts the table; the per-parameter mask is rebuilt here ([P], not [n_cp])
-  int rc = fill_penalty(prog, pen, p, &unused, st);
-  if (unused) cudaFreeAsync(unused, st);
+  int rc;
+  {
+    Scratch sc;
+    sc.st = st;
+    rc = fill_penalty(prog, pen, p, sc);
+  }
   if (rc) return rc;
   uint8_t* mask_dev = nullptr;
   if (p.pen.kind != CPF_PEN_NONE && prog->n_params > 0) {
@@ -721,6 +788,14 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss, const cpf_p
   const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
   CPF_DISPATCH(dtype, (run_adam<R>(p, loss, penalty, adam, batch, step0, num_steps, buf,
                                    (cudaStream_t)stream)));
+}
+
+int cpf_workspace_bytes(const cpf_program* prog, int32_t loss_kind, int32_t dtype, int64_t batch, int64_t* bytes) {
+  if (!prog || !bytes || batch < 0) return fail(CPF_ERR_INVALID, "NULL argument / negative batch");
+  if (loss_kind < CPF_LOSS_HS || loss_kind > CPF_LOSS_RELPHASE) return fail(CPF_ERR_INVALID, "unknown loss kind");
+  const cpf::Program* p = reinterpret_cast<const cpf::Program*>(prog);
+  *bytes = dtype == CPF_F64 ? workspace_bytes_t<double>(p, loss_kind, batch) : workspace_bytes_t<float>(p, loss_kind, batch);
+  return CPF_OK;
 }
 
 int cpf_adam_step(const cpf_program* prog, const cpf_penalty_spec* penalty, const cpf_adam_spec* adam, int32_t dtype,

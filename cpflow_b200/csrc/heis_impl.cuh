@@ -29,6 +29,7 @@
 // Per sample and eval for C3 (n = 4, K = 40): ~5.6 k warp instructions (x 1/4 warp) instead of ~22 k.
 #pragma once
 #include <atomic>
+#include <cmath>
 
 #include "engine_impl.cuh"
 
@@ -735,17 +736,16 @@ constexpr int AXP_ZXZ = 2 | (0 << 4) | (2 << 8);
 constexpr int AXP_XYZ = 0 | (1 << 4) | (2 << 8);
 constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
 
-// gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined
+// gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined.  ga / gb: the loads of
+// the first two gates, issued by the caller at the top of the parameter phase together with the first loads of the
+// other gate classes (one exposed L2 round trip per step instead of one per class).
 template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, Pk4<R>* pk, int g0,
-                                              int g_end, int stride, R* coef, R* aux) {
+                                              int g_end, int stride, R* coef, R* aux, GateIn<R> ga, GateIn<R> gb) {
   constexpr int SW = HEIS_SU2_WORDS;
   // Two gates in flight, loop unrolled by two so that the buffers keep their registers (no copies at the back
   // edge): the state of gate g + 2 stride is requested as soon as gate g is done and has the whole update of
   // gate g + stride to arrive (the L2 round trip is about as long as one gate's update).
-  GateIn<R> ga = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
-  GateIn<R> gb = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride,
-                                coef + SW * (g0 + stride), aux + 4 * (g0 + stride));
 #pragma unroll 1
   for (int g = g0; g < g_end; g += 2 * stride) {
     heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, ga, coef + SW * g, aux + 4 * g);
@@ -760,15 +760,25 @@ __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* m
 template <typename R>
 __device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const HSu2* ms,
                                                   const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end, int stride, R* coef,
-                                                  R* aux) {
+                                                  R* aux, const GateIn<R>& ga, const GateIn<R>& gb) {
   if (axp == AXP_XYZ) {
-    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-    else heis_su2_loop<R, 0, 1, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
+    else heis_su2_loop<R, 0, 1, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
   } else if (axp == AXP_ZXZ) {
-    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-    else heis_su2_loop<R, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-  else heis_su2_loop<R, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
+    else heis_su2_loop<R, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
+  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
+  else heis_su2_loop<R, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
+}
+// first two loads of a gate class (see heis_su2_loop)
+template <typename R>
+__device__ __forceinline__ void heis_su2_prologue(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, const Pk4<R>* pk,
+                                                  int g0, int g_end, int stride, const R* coef, const R* aux,
+                                                  GateIn<R>& ga, GateIn<R>& gb) {
+  constexpr int SW = HEIS_SU2_WORDS;
+  ga = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
+  gb = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride, coef + SW * (g0 + stride),
+                      aux + 4 * (g0 + stride));
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -886,16 +896,21 @@ heis_kernel(const KParams<R> p) {
       // surface gates (slots < NQ) and block gates (the rest) each share one axis pattern in the templates
       // plain: an Adam pass (not the first, coefficient-only one) without freeze mask and parameter history
       const bool plain = phase == PH_ADAM && p.freeze == nullptr && p.hist_params == nullptr;
-      heis_su2_loop_any(p.axp_surface, plain, p, s_su2, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
-      heis_su2_loop_any(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
+      // the first loads of all three gate classes go out together: one exposed L2 round trip per step
+      const int n_surf = NQ < p.n_su2 ? NQ : p.n_su2;
+      GateIn<R> sa, sb, ba, bb;
+      heis_su2_prologue(p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux, ba, bb);
+      int k = m;
+      int pi_n = -1;
+      Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
+      HCp md_n = HCp{-1, 0, 0, 0};
+      if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
+      heis_su2_prologue(p, s_su2, u, pk, m, n_surf, TPS, coef, aux, sa, sb);
+      heis_su2_loop_any(p.axp_surface, plain, p, s_su2, u, pk, m, n_surf, TPS, coef, aux, sa, sb);
+      heis_su2_loop_any(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux, ba, bb);
       // entangler angles, software pipelined like the fused-gate loops: the packed state of the next gate is
       // requested before the current one is processed
       {
-        int k = m;
-        int pi_n = -1;
-        Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
-        HCp md_n = HCp{-1, 0, 0, 0};
-        if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
 #pragma unroll 1
         for (; k < p.n_cp; k += TPS) {
           const HCp md = md_n;
@@ -1113,13 +1128,16 @@ inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sa
 // (sample, chunk) items are laid on a ring in sample-major order, and consecutive launches of `slots` items each walk
 // along it.  All launches but the last run at full residency; stream order guarantees that chunk v + 1 of a sample
 // starts after its chunk v has been written back (the run is resumable by construction: split runs are bit-identical
-// to one run).  Predicted time per step of a launch with s resident samples per SM: a + b s with a / b = 28 samples
-// (measured: 16 -> 42 M, 28 -> 58 M, 43 -> 71 M, 60 -> 79 M evals/s); a launch costs about one more step (state
-// pack / unpack, coefficient pass) plus the drift between CTAs that
-// a launch boundary exposes, about 3.5 % of its steps (measured: 10^5 samples in 43 launches of 500 steps lose 4 %,
-// 12 500 samples in 33 launches of 80 steps gain 15 % over two 2/3-full rounds).
+// to one run).
+// The choice is an empirical throughput model fitted to B200 measurements of the C3 kernel (profiles/r2_*perf*):
+//   one launch      relative rate (s / s_full)^0.7 for s resident samples per SM, times a tail factor
+//                   1 - 0.05 min(1, 3 / rounds) (a CTA runs all T steps, so with few rounds the SMs that finish first
+//                   idle: 10^5 samples in 11 rounds 121 M evals/s, 5 x 10^4 in 6 rounds 111 M, 2.5 x 10^4 in 3: 109 M,
+//                   1.25 x 10^4 in 2 rounds of 43: 102 M)
+//   sliced          1 / (1.035 + 3 / C) for chunks of C steps (drift between CTAs exposed at every launch boundary,
+//                   state pack / unpack and the coefficient pass), times the fill of the last launch
+//                   (116-118 M evals/s at every batch size measured).
 struct HeisSlicing { int k; long long slots; };
-inline double heis_step_cost(double samples_per_sm) { return 1.0 + samples_per_sm / 28.0; }
 inline HeisSlicing heis_slicing(long long B, int nsteps, size_t fixed_bytes, size_t per_sample, int tps, int maxt, int regs,
                                 int n_sm, bool allowed) {
   HeisSlicing best{1, 0};
@@ -1129,33 +1147,21 @@ inline HeisSlicing heis_slicing(long long B, int nsteps, size_t fixed_bytes, siz
   int forced = -1;
   if (const char* e = getenv("CPF_HEIS_SLICES")) forced = atoi(e);
   if (!allowed || forced == 0 || forced == 1 || B <= 0 || nsteps < 2) return best;
-  auto cost = [&](int k) {
-    if (k == 1) {
-      const HeisGeometry g = heis_geometry(B, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
-      const long long rounds = (g.grid + (long long)g.ctas * n_sm - 1) / ((long long)g.ctas * n_sm);
-      return (double)rounds * (nsteps + 3) * heis_step_cost((double)g.spb * g.ctas);
-    }
-    const long long items = B * k, fullw = items / slots, rest = items % slots;
-    const double C = 1.035 * (nsteps / k) + 3.0;
-    double t = (double)fullw * C * heis_step_cost((double)full.spb * full.ctas);
-    if (rest) {
-      const HeisGeometry g = heis_geometry(rest, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
-      const long long rounds = (g.grid + (long long)g.ctas * n_sm - 1) / ((long long)g.ctas * n_sm);
-      t += (double)rounds * C * heis_step_cost((double)g.spb * g.ctas);
-    }
-    return t;
-  };
   // a ring shorter than one launch would put two visits of a sample into the same launch: never sliced
   if (B <= slots) return best;
   if (forced > 1) {
     if (nsteps % forced == 0) best.k = forced;
     return best;
   }
-  double tb = cost(1);
+  const HeisGeometry g1 = heis_geometry(B, fixed_bytes, per_sample, tps, maxt, regs, n_sm);
+  const long long rounds = (g1.grid + (long long)g1.ctas * n_sm - 1) / ((long long)g1.ctas * n_sm);
+  const double occ = (double)g1.spb * g1.ctas / ((double)full.spb * full.ctas);
+  double rate_best = pow(occ < 1.0 ? occ : 1.0, 0.7) * (1.0 - 0.05 * (rounds >= 3 ? 3.0 / (double)rounds : 1.0));
   for (int k = 2; k <= 64 && nsteps / k >= 20; ++k) {
     if (nsteps % k) continue;
-    const double t = cost(k);
-    if (t < tb * 0.995) { tb = t; best.k = k; }
+    const double launches = (double)(B * k) / (double)slots;
+    const double rate = 1.0 / (1.035 + 3.0 / (nsteps / k)) * launches / ceil(launches);
+    if (rate > rate_best * 1.01) { rate_best = rate; best.k = k; }
   }
   return best;
 }

@@ -2,6 +2,7 @@
 pointers on torch's current stream.  No computation happens here."""
 import ctypes as C
 import math
+import warnings
 
 import numpy as np
 import torch
@@ -72,11 +73,30 @@ class Program:
         L.check(L.load().cpf_eval_cost(self._h, int(loss_kind), _DT[dtype], C.byref(f), C.byref(b)))
         return f.value, b.value
 
+    def _note_engine(self, loss, dtype, batch):
+        """One warning per program when a Hilbert-Schmidt run does not land on the Heisenberg-picture kernel (a
+        non-block-structured gate list, 5 qubits in complex128, more than 32767 parameters or B * P >= 2^32): the
+        state-adjoint kernels give the same numbers about five times slower."""
+        if loss.kind != "hs" or getattr(self, "_warned_engine", False) or self.n_qubits > 5:
+            return
+        if self.launch_plan(max(1, int(batch)), L.LOSS_HS, dtype)["engine"] == 0:
+            self._warned_engine = True
+            warnings.warn(f"cpflow_b200: this {self.n_qubits}-qubit program ({self.info['n_ops']} gates, {dtype}) runs its "
+                          "Hilbert-Schmidt loss on the state-adjoint kernels, not on the Heisenberg-picture kernel "
+                          "(see Program._note_engine)", RuntimeWarning, stacklevel=3)
+
     def executed_cost(self, loss_kind=L.LOSS_HS, dtype=torch.float32):
         """Floating-point operations per evaluation the chosen kernel executes (cpf_executed_cost)."""
         f = C.c_double()
         L.check(L.load().cpf_executed_cost(self._h, int(loss_kind), _DT[dtype], C.byref(f)))
         return f.value
+
+    def workspace_bytes(self, batch, loss_kind=L.LOSS_HS, dtype=torch.float32):
+        """Device scratch one adam_run on `batch` samples needs (cpf_workspace_bytes); give AdamState.workspace a
+        uint8 CUDA tensor of that size to keep the library out of the allocator."""
+        n = C.c_int64()
+        L.check(L.load().cpf_workspace_bytes(self._h, int(loss_kind), _DT[dtype], int(batch), C.byref(n)))
+        return n.value
 
     def launch_plan(self, batch, loss_kind=L.LOSS_HS, dtype=torch.float32, n_sm=0, regs_per_thread=0):
         """The launch geometry the engine would use for `batch` samples (cpf_launch_plan; needs no device)."""
@@ -104,6 +124,8 @@ class Program:
         gr = torch.empty(B, self.n_params, dtype=dt, device=angles.device) if want_grad else None
         ls = loss.spec(dt, angles.device)
         ps = penalty.spec() if penalty is not None else None
+        if want_grad:          # loss-only evaluation of arbitrary gate lists (refine) is the state kernels' job
+            self._note_engine(loss, dt, B)
         with _on(angles):
             L.check(L.load().cpf_loss_grad(self._h, C.byref(ls), C.byref(ps) if ps is not None else None,
                                            _DT[dt], B, _ptr(angles), _ptr(lo), _ptr(rg), _ptr(gr), _stream()))
@@ -151,6 +173,7 @@ class Program:
         ps = penalty.spec() if penalty is not None else None
         ad = L.CpfAdamSpec(float(lr), float(b1), float(b2), float(eps))
         buf = state.buffers()
+        self._note_engine(loss, dt, state.batch)
         with _on(state.angles):
             L.check(L.load().cpf_adam_run(self._h, C.byref(ls), C.byref(ps) if ps is not None else None,
                                           C.byref(ad), _DT[dt], state.batch, state.step, int(num_steps),
@@ -198,13 +221,15 @@ class AdamState:
         self.hist_params = angles[:, None, :].repeat(1, hist_len, 1).contiguous() if hist_len else None
         self.hist_regloss = torch.zeros(B, hist_len, dtype=dt, device=dev) if hist_len else None
         self.step = 0
+        self.workspace = None      # optional caller-owned scratch (uint8 CUDA tensor), see Program.workspace_bytes
 
     def buffers(self):
         return L.CpfAdamBuffers(
             _ptr(self.angles).value, _ptr(self.m).value, _ptr(self.v).value, _ptr(self.freeze).value,
             _ptr(self.best_params).value, _ptr(self.best_regloss).value, _ptr(self.best_reg).value,
             _ptr(self.init_regloss).value, _ptr(self.init_reg).value, _ptr(self.hist_params).value,
-            _ptr(self.hist_regloss).value, self.hist_len)
+            _ptr(self.hist_regloss).value, self.hist_len, _ptr(self.workspace).value,
+            self.workspace.numel() if self.workspace is not None else 0)
 
 
 class Loss:

@@ -141,6 +141,11 @@ typedef struct cpf_adam_buffers {
   void* hist_params;       /* nullable [B,hist_len,P]: row i+1 = theta_{i+1} (optimization.py:52-59) */
   void* hist_regloss;      /* nullable [B,hist_len]:   row i   = regloss(theta_i) */
   int64_t hist_len;        /* number of history rows (the run's total num_iterations) */
+  void* workspace;         /* nullable: 256-byte aligned device scratch of at least cpf_workspace_bytes(...) bytes,
+                              owned by the caller.  NULL: the library takes its scratch from the device's
+                              stream-ordered memory pool on `stream` (and, once per device, raises that pool's
+                              release threshold so the blocks are kept between calls) */
+  int64_t workspace_bytes;
 } cpf_adam_buffers;
 
 int cpf_version(void);
@@ -182,6 +187,11 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss,
                  const cpf_penalty_spec* penalty, const cpf_adam_spec* adam, int32_t dtype,
                  int64_t batch, int64_t step0, int64_t num_steps, const cpf_adam_buffers* buf,
                  void* stream);
+
+/* Device scratch one cpf_adam_run (or cpf_loss_grad) call on `batch` samples needs: the packed optimiser state
+ * (16 bytes per parameter and sample on the Heisenberg-picture kernel), the staged target and the penalty mask.
+ * Callers that manage device memory themselves allocate this once and pass it in cpf_adam_buffers.workspace. */
+int cpf_workspace_bytes(const cpf_program* prog, int32_t loss_kind, int32_t dtype, int64_t batch, int64_t* bytes);
 
 /* One iteration of the same loop for a loss that is evaluated OUTSIDE the engine (an arbitrary user
  * `unitary_loss_func(U)`, cpflow/main.py:528-529): the caller evaluates loss[B] on cpf_unitary's output and gets

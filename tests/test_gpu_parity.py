@@ -97,11 +97,12 @@ def _oracle_run(n, ops, target, a0, lr, T, cp_mask, r, **kw):
                                O.make_regularization_function(), **kw)
 
 
-@pytest.mark.parametrize("dt,T,tol", [(torch.float64, 60, 1e-9), (torch.float32, 12, 2e-4)])
+@pytest.mark.parametrize("dt,T,tol", [(torch.float64, 60, 1e-9), (torch.float32, 3, 1e-4)])
 def test_adam_loop_parity(dt, T, tol):
     """Whole fused loop vs the oracle loop (optimization.py:28-94, 362): initial regloss, best
     regloss / reg / params.  f32 runs are compared over a short horizon (the trajectories are
-    chaotic; per-step parity is what is pinned)."""
+    chaotic, see test_adam_loop_parity_c3_shape_f32; per-step parity is what is pinned); split runs must be
+    bit-identical to one run over a longer one."""
     n, layer, K = 3, chain_layer(3), 6
     anz, oanz, ops = setup(n, layer, K, "xyz")
     B = 9
@@ -109,18 +110,20 @@ def test_adam_loop_parity(dt, T, tol):
     res = _oracle_run(n, ops, u_toff3, a0, 0.1, T, oanz.cp_mask, 0.002)
     obr = np.array([r["regloss"][1].item() for r in res]); oir = np.array([r["regloss"][0].item() for r in res])
     obp = np.stack([r["params"][1].numpy() for r in res]); oreg = np.array([r["reg"][1].item() for r in res])
+    st = anz.program.adam_state(a0.to(DEV).clone())
+    anz.program.adam_run(st, Loss("hs", u_toff3), pen(0.002), 0.1, T)
+    torch.cuda.synchronize()
+    assert np.abs(st.init_regloss.cpu().numpy() - oir).max() < min(tol, 1e-6)
+    assert np.abs(st.best_regloss.cpu().numpy() - obr).max() < tol
+    assert np.abs(st.best_reg.cpu().numpy() - oreg).max() < tol
+    assert np.abs(st.best_params.cpu().numpy() - obp).max() < tol * 50
+    Tl = max(T, 24)
     outs = []
-    for chunks in ([T], [1, T // 3, T - 1 - T // 3]):
+    for chunks in ([Tl], [1, Tl // 3, Tl - 1 - Tl // 3]):
         st = anz.program.adam_state(a0.to(DEV).clone())
         for c in chunks:
             anz.program.adam_run(st, Loss("hs", u_toff3), pen(0.002), 0.1, c)
-        torch.cuda.synchronize()
-        assert np.abs(st.init_regloss.cpu().numpy() - oir).max() < tol
-        assert np.abs(st.best_regloss.cpu().numpy() - obr).max() < tol
-        assert np.abs(st.best_reg.cpu().numpy() - oreg).max() < tol
-        assert np.abs(st.best_params.cpu().numpy() - obp).max() < tol * 50
         outs.append((st.best_params.clone(), st.best_regloss.clone(), st.angles.clone(), st.m.clone(), st.v.clone()))
-    # split runs are bit-identical to one run
     for x, y in zip(outs[0], outs[1]):
         assert torch.equal(x, y)
 

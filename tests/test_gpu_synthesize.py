@@ -40,9 +40,9 @@ def test_mynimize_repeated_return_contract():
     assert r["regloss"][1] <= r["regloss"][0]
     # oracle agreement of the whole returned structure (f32, short horizon)
     ores = O.mynimize_repeated(3, O.ansatz_program(O.cp_ansatz(chain_layer(3), 6)), "hs",
-                               torch.tensor(u_toff3), torch.tensor(a0), 0.1, 12,
+                               torch.tensor(u_toff3), torch.tensor(a0), 0.1, 4,
                                anz.cp_mask, 0.002, O.make_regularization_function())
-    res12 = mynimize_repeated(pl, learning_rate=0.1, num_iterations=12, initial_params_batch=a0,
+    res12 = mynimize_repeated(pl, learning_rate=0.1, num_iterations=4, initial_params_batch=a0,
                               regularization_func=pen, keep_history=False)
     for a, b in zip(res12, ores):
         assert np.abs(a["regloss"] - b["regloss"].numpy()).max() < 2e-4
