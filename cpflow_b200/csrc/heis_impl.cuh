@@ -74,7 +74,10 @@ struct HCfg {
   static constexpr int XR = 1 << PB;
   static constexpr int TPS = N / CPT;           // threads per sample
   // forward state registers: 2 * N * CPT words (x2 for double) -> register cap 128 (512 threads) or 255 (256)
-  static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? 512 : 256;
+#ifndef CPF_F64_MAXT
+#define CPF_F64_MAXT 512
+#endif
+  static constexpr int MAXT = 2 * N * CPT * (int)(sizeof(R) / 4) <= 64 ? (sizeof(R) == 8 && NQ >= 4 ? CPF_F64_MAXT : 512) : 256;
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");
 };
 
@@ -696,7 +699,7 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
   const int ax0 = AX0 == -2 ? (a0 == 15 ? -1 : a0) : AX0;
   const int ax1 = AX0 == -2 ? (a1 == 15 ? -1 : a1) : AX1;
   const int ax2 = AX0 == -2 ? (a2 == 15 ? -1 : a2) : AX2;
-  if (PLAIN || u.phase != PH_COEF) {
+  if (u.phase != PH_COEF) {
     // chain rule through G = R_2 R_1 R_0: g_2 = S . e_2, g_1 = S . (R_2 e_1) = (R_2^T S) . e_1,
     // g_0 = (R_1^T R_2^T S) . e_0: rotate S backwards (no products with the zero entries of unit vectors)
     const R C2 = in.c2 * in.c2 - in.s2 * in.s2, S2 = R(2) * in.c2 * in.s2;
@@ -736,16 +739,19 @@ constexpr int AXP_ZXZ = 2 | (0 << 4) | (2 << 8);
 constexpr int AXP_XYZ = 0 | (1 << 4) | (2 << 8);
 constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
 
-// gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined.  ga / gb: the loads of
-// the first two gates, issued by the caller at the top of the parameter phase together with the first loads of the
-// other gate classes (one exposed L2 round trip per step instead of one per class).
+// gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined.  (Issuing the first loads of
+// all three gate classes together at the top of the parameter phase was measured: no gain in float - 121.6 vs 121.3 M
+// evals/s on C3 - and 1.5 KB of spills in the double kernels; each loop keeps its own prologue.)
 template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
 __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, Pk4<R>* pk, int g0,
-                                              int g_end, int stride, R* coef, R* aux, GateIn<R> ga, GateIn<R> gb) {
+                                              int g_end, int stride, R* coef, R* aux) {
   constexpr int SW = HEIS_SU2_WORDS;
   // Two gates in flight, loop unrolled by two so that the buffers keep their registers (no copies at the back
   // edge): the state of gate g + 2 stride is requested as soon as gate g is done and has the whole update of
   // gate g + stride to arrive (the L2 round trip is about as long as one gate's update).
+  GateIn<R> ga = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
+  GateIn<R> gb = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride,
+                                coef + SW * (g0 + stride), aux + 4 * (g0 + stride));
 #pragma unroll 1
   for (int g = g0; g < g_end; g += 2 * stride) {
     heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, ga, coef + SW * g, aux + 4 * g);
@@ -760,25 +766,15 @@ __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* m
 template <typename R>
 __device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const HSu2* ms,
                                                   const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end, int stride, R* coef,
-                                                  R* aux, const GateIn<R>& ga, const GateIn<R>& gb) {
+                                                  R* aux) {
   if (axp == AXP_XYZ) {
-    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
-    else heis_su2_loop<R, 0, 1, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
+    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    else heis_su2_loop<R, 0, 1, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
   } else if (axp == AXP_ZXZ) {
-    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
-    else heis_su2_loop<R, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
-  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
-  else heis_su2_loop<R, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux, ga, gb);
-}
-// first two loads of a gate class (see heis_su2_loop)
-template <typename R>
-__device__ __forceinline__ void heis_su2_prologue(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, const Pk4<R>* pk,
-                                                  int g0, int g_end, int stride, const R* coef, const R* aux,
-                                                  GateIn<R>& ga, GateIn<R>& gb) {
-  constexpr int SW = HEIS_SU2_WORDS;
-  ga = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
-  gb = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride, coef + SW * (g0 + stride),
-                      aux + 4 * (g0 + stride));
+    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    else heis_su2_loop<R, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+  else heis_su2_loop<R, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -894,23 +890,21 @@ heis_kernel(const KParams<R> p) {
         u.ibc1 = R(1) / u.bc1; u.ibc2 = R(1) / u.bc2;
       }
       // surface gates (slots < NQ) and block gates (the rest) each share one axis pattern in the templates
-      // plain: an Adam pass (not the first, coefficient-only one) without freeze mask and parameter history
-      const bool plain = phase == PH_ADAM && p.freeze == nullptr && p.hist_params == nullptr;
-      // the first loads of all three gate classes go out together: one exposed L2 round trip per step
-      const int n_surf = NQ < p.n_su2 ? NQ : p.n_su2;
-      GateIn<R> sa, sb, ba, bb;
-      heis_su2_prologue(p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux, ba, bb);
-      int k = m;
-      int pi_n = -1;
-      Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
-      HCp md_n = HCp{-1, 0, 0, 0};
-      if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
-      heis_su2_prologue(p, s_su2, u, pk, m, n_surf, TPS, coef, aux, sa, sb);
-      heis_su2_loop_any(p.axp_surface, plain, p, s_su2, u, pk, m, n_surf, TPS, coef, aux, sa, sb);
-      heis_su2_loop_any(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux, ba, bb);
+      // plain: an Adam RUN without freeze mask and parameter history.  Every pass of such a run, the first
+      // (coefficient-only) one of a launch included, goes through the same PLAIN instantiation of the gate loops:
+      // split and time-sliced runs are bit-identical to one launch by construction, not by the compiler's choice of
+      // identical FMA contractions in two instantiations
+      const bool plain = p.mode == M_ADAM && p.freeze == nullptr && p.hist_params == nullptr;
+      heis_su2_loop_any(p.axp_surface, plain, p, s_su2, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
       // entangler angles, software pipelined like the fused-gate loops: the packed state of the next gate is
       // requested before the current one is processed
       {
+        int k = m;
+        int pi_n = -1;
+        Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
+        HCp md_n = HCp{-1, 0, 0, 0};
+        if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
 #pragma unroll 1
         for (; k < p.n_cp; k += TPS) {
           const HCp md = md_n;

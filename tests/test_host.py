@@ -38,7 +38,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(L.CpfProgramInfo) == 32
     assert C.sizeof(L.CpfAdamSpec) == 32
     assert C.sizeof(L.CpfPenaltySpec) == 8 + 16 + 4 * 8 * L.MAX_SEGMENTS + 8
-    assert C.sizeof(L.CpfAdamBuffers) == 12 * 8
+    assert C.sizeof(L.CpfAdamBuffers) == 14 * 8
+    assert C.sizeof(L.CpfLaunchInfo) == 8 * 4 + 3 * 8
 
 
 def _create(lib, n, ops, P):
@@ -276,3 +277,17 @@ def test_oracle_normal_sampler():
     cp_draws = a[:, mask == 1]
     assert abs(cp_draws.mean()) < 0.05 and abs(cp_draws.std() - 1.5) < 0.05
     assert np.array_equal(a[:, mask == 0], u[:, mask == 0])
+
+
+def test_workspace_query_without_a_device(lib):
+    """cpf_workspace_bytes needs no device: 16 bytes per parameter and sample of packed optimiser state on the
+    Heisenberg kernel (32 in complex128), a staged target only on the state-adjoint kernels."""
+    import torch
+    anz = A.Ansatz(4, "cp", T.fill_layers(T.chain_layer(4), 40))
+    P = anz.num_angles
+    w32 = anz.program.workspace_bytes(1000)
+    w64 = anz.program.workspace_bytes(1000, dtype=torch.float64)
+    assert 16 * 1000 * P <= w32 <= 16 * 1000 * P + 16 * 1000 * 88 + 8192
+    assert 32 * 1000 * P <= w64 <= 2 * w32 + 8192
+    assert anz.program.workspace_bytes(1000, L.LOSS_STATE) < 4096
+    assert anz.program.workspace_bytes(0) >= 0

@@ -47,7 +47,7 @@ if t_rows:
     agg = collections.Counter()
     n_launch = set()
     for r in t_rows[1:]:
-        if "heis_kernel" in r[iK]:
+        if "heis_kernel" in r[iK] and "pack_target" not in r[iK]:
             agg[r[iM]] += float(r[iV].replace(",", ""))
             n_launch.add(r[h.index("ID")])
     launches.append({"kernel": "cpf::heis_kernel<float,4,2,HeisSweep<chain>>", "samples": samples, "iters": iters,
