@@ -234,8 +234,11 @@ void heis_scratch_sizes(const cpf::Program* prog, int64_t batch, size_t* target_
   const int words = cpf::heis_target_words<R>(prog->n_qubits, cpt);
   *target_bytes = ((size_t)words * sizeof(R) + 15) & ~(size_t)15;
   const size_t aux_bytes = (size_t)batch * (prog->su2.empty() ? 1 : prog->su2.size()) * 4 * sizeof(R);
-  *aux_pad = (aux_bytes + 31) & ~(size_t)31;
-  *pk_bytes = (size_t)batch * (prog->n_params > 0 ? prog->n_params : 1) * 4 * sizeof(R);
+  *aux_pad = (aux_bytes + 255) & ~(size_t)255;      // the packed state starts on a 256-byte boundary (blocks of 16 positions)
+  // lane-interleaved packed optimiser state (heis_impl.cuh: heis_pk_stride words per sample)
+  const int tps = (1 << prog->n_qubits) / cpt;
+  *pk_bytes = (size_t)batch * (size_t)cpf::heis_pk_stride(prog->n_qubits, tps, (int)prog->su2.size(), (int)prog->cp.size()) *
+              sizeof(R);
 }
 
 template <typename R>
@@ -276,6 +279,16 @@ int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams
   for (int q = 0; q < 8; ++q) p.last_slot[q] = q < prog->n_qubits ? prog->last_slot[q] : 0;
   p.axp_surface = pattern(0, (size_t)prog->n_qubits);
   p.axp_block = pattern((size_t)prog->n_qubits, prog->su2.size());
+  p.su2_all_params = 1;
+  int referenced = 0;
+  for (const cpf::Su2Meta& md : prog->su2)
+    for (int k = 0; k < 3; ++k) {
+      if (md.axis[k] >= 0 && md.pidx[k] < 0) p.su2_all_params = 0;
+      if (md.pidx[k] >= 0) ++referenced;
+    }
+  for (const cpf::CpMeta& md : prog->cp) if (md.pidx >= 0) ++referenced;
+  p.unreferenced_params = referenced != prog->n_params;      // (a parameter feeds at most one gate: program.cpp)
+  p.pk_stride = cpf::heis_pk_stride(prog->n_qubits, (1 << prog->n_qubits) / cpt, (int)prog->su2.size(), (int)prog->cp.size());
   return CPF_OK;
 }
 

@@ -58,7 +58,7 @@ struct KParams {
   R* hist_params; R* hist_regloss; long long hist_len;
   R* loss_out; R* reg_out; R* grad_out;
   R* u_out; const R* cot;
-  void* pk;         // heis_kernel: [B][P] packed optimiser state {theta, m, v, best} (heis_impl.cuh: Pk4)
+  void* pk;         // heis_kernel: [B][pk_stride] lane-interleaved optimiser state {theta, m, v, best} (heis_impl.cuh: Pk4)
   R* aux;           // heis_kernel: [B][n_su2][4] half-angle cos/sin of the 2nd and 3rd fused rotations
   int coef_stride;  // R words per sample in shared memory
   int spb;          // heis_kernel: sample slots used per CTA
@@ -69,6 +69,9 @@ struct KParams {
   long long ring_start, ring_end;
   int colmode;      // engine_kernel<SINGLE>, M_UNITARY: virtual sample b = (sample b / N, column b % N)
   int axp_surface, axp_block;   // heis_kernel: packed rotation axes shared by the surface / block gates
+  int su2_all_params;           // heis_kernel: every rotation of every fused gate is a parameter (no constant angles)
+  int unreferenced_params;      // heis_kernel: some parameters feed no gate
+  int pk_stride;                // heis_kernel: words of R per sample in the packed optimiser state (heis_pk_stride)
   int last_slot[8];             // heis_kernel: slot of the last fused gate on each qubit
   PenaltyT<R> pen;
 };

@@ -175,8 +175,8 @@ struct HeisSweep {
     surface_fwd<0>(yr, yi, coef);
     const int K = p.n_cp;
     const R* cs = coef + SW * NQ;
-#pragma unroll 1
     if (lb.fwd) __syncthreads();
+#pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += NBL) {
       blocks_fwd<0>(k0, K, cs, yr, yi);
       cs += 2 * SW * NBL;
@@ -521,24 +521,44 @@ struct UpdCtx {
   R bc1, bc2, ibc1, ibc2;
 };
 
-// Optimiser state of one parameter, packed so that the update phase moves it with one 16-byte (float) or two
-// 16-byte (double) accesses: theta, Adam moments, best-regloss parameter.  The kernel packs the caller's
-// separate arrays (include/cpflow_b200.h: cpf_adam_buffers) into this scratch at launch and unpacks at the end.
-template <typename R> struct __align__(4 * sizeof(R) > 16 ? 16 : 4 * sizeof(R)) Pk4 { R th, mu, nu, best; };
-__device__ __forceinline__ Pk4<float> pk_load(const Pk4<float>* q) {
-  const float4 t = *reinterpret_cast<const float4*>(q);
-  return {t.x, t.y, t.z, t.w};
+// Optimiser state {theta, m, v, best} of a sample in the kernel's scratch, LANE-INTERLEAVED: the update phase is bound by
+// the L1 -> L2 request port (one 32-byte sector per cycle and SM), so the layout makes every access of a warp cover
+// whole sectors.  A parameter has a POSITION q (heis_pk_pos_*) chosen so that the parameters the lanes of a sample
+// touch in the same instruction are neighbours; positions are stored in blocks of 16: word (q >> 4) * 64 + f * 16 +
+// (q & 15) holds field f (0 theta, 1 m, 2 v, 3 best-regloss parameter) of position q.  A fused gate g, rotation j:
+//   surface gates (g < n):      q = (j TPS + g) 2                                  (lane g, one gate per lane)
+//   block gates (gb = g - n):   q = 6 TPS + (((i >> 1) 3 + j) TPS + m) 2 + (i & 1),  m = gb % TPS, i = gb / TPS
+// i.e. the two gates (i even, i odd) a lane updates side by side (heis_pair_update) are the two halves of an aligned
+// 8-byte pair and the 8 lanes of a 4-qubit sample read one contiguous 64-byte row per field.  Entangler k follows at
+// cp_base + k.  The kernel packs the caller's separate arrays (include/cpflow_b200.h: cpf_adam_buffers) into this
+// scratch at launch and unpacks at the end; `best` is only ever written (when a step improved), never read back
+// before the unpack.
+__host__ __device__ inline int heis_pk_pos_su2(int g, int j, int nq, int tps) {
+  if (g < nq) return (j * tps + g) * 2;
+  const int gb = g - nq, m = gb % tps, i = gb / tps;
+  return 6 * tps + (((i >> 1) * 3 + j) * tps + m) * 2 + (i & 1);
 }
-__device__ __forceinline__ void pk_store(Pk4<float>* q, const Pk4<float>& v) {
-  *reinterpret_cast<float4*>(q) = make_float4(v.th, v.mu, v.nu, v.best);
+__host__ __device__ inline int heis_pk_pair_iters(int nq, int tps, int n_su2) {
+  const int nb = n_su2 > nq ? n_su2 - nq : 0;
+  return (nb + 2 * tps - 1) / (2 * tps);
 }
-__device__ __forceinline__ Pk4<double> pk_load(const Pk4<double>* q) {
-  const double2 a = reinterpret_cast<const double2*>(q)[0], b = reinterpret_cast<const double2*>(q)[1];
-  return {a.x, a.y, b.x, b.y};
+__host__ __device__ inline int heis_pk_cp_base(int nq, int tps, int n_su2) {
+  return 6 * tps + heis_pk_pair_iters(nq, tps, n_su2) * 6 * tps;
 }
-__device__ __forceinline__ void pk_store(Pk4<double>* q, const Pk4<double>& v) {
-  reinterpret_cast<double2*>(q)[0] = make_double2(v.th, v.mu);
-  reinterpret_cast<double2*>(q)[1] = make_double2(v.nu, v.best);
+// words (of R) per sample
+__host__ __device__ inline int heis_pk_stride(int nq, int tps, int n_su2, int n_cp) {
+  return ((heis_pk_cp_base(nq, tps, n_su2) + n_cp + 15) & ~15) * 4;
+}
+template <typename R> struct Pk4 { R th, mu, nu, best; };
+template <typename R> __device__ __forceinline__ R* pk_at(R* pk, int q) { return pk + ((q >> 4) << 6) + (q & 15); }
+template <typename R> __device__ __forceinline__ const R* pk_at(const R* pk, int q) { return pk + ((q >> 4) << 6) + (q & 15); }
+template <typename R> __device__ __forceinline__ Pk4<R> pk_load(const R* pk, int q) {
+  const R* b = pk_at(pk, q);
+  return {b[0], b[16], b[32], R(0)};
+}
+template <typename R> __device__ __forceinline__ void pk_store(R* pk, int q, const Pk4<R>& v) {
+  R* b = pk_at(pk, q);
+  b[0] = v.th; b[16] = v.mu; b[32] = v.nu;
 }
 
 // MUFU approximations (rsqrt: 2^-22.4, rcp: 1 ulp) refined by one Newton step: the unit phases of the ZYZ data are
@@ -627,17 +647,18 @@ __device__ __forceinline__ void adam_inl(const KParams<float>& p, const UpdCtx<f
 // one parameter: gradient sink (loss_grad mode) or best-parameter bookkeeping + Adam step on the packed state
 // PLAIN: Adam pass of a launch without freeze mask and parameter history (the stage-1 runs of Synthesize.static()):
 // the per-parameter tests on those pointers disappear from the gate loops.
+// pi: parameter index (the caller's arrays), q: its position in the packed state
 template <typename R, bool PLAIN>
-__device__ __forceinline__ void heis_apply(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, int pi, R g, Pk4<R>& v) {
+__device__ __forceinline__ void heis_apply(const KParams<R>& p, const UpdCtx<R>& u, R* pk, int pi, int q, R g, Pk4<R>& v) {
   if (!PLAIN && u.phase == PH_GRAD) {
     if (u.active) p.grad_out[u.off + (unsigned)pi] = g;
     return;
   }
   // v.th is still the pre-update parameter of the step being finished (optimization.py:70-73)
-  if (u.store_best) v.best = v.th;
+  if (u.store_best && u.active) pk_at(pk, q)[48] = v.th;
   if (PLAIN || !(p.freeze && p.freeze[u.off + (unsigned)pi])) adam_inl(p, u, g, v.th, v.mu, v.nu);
   if (u.active) {
-    pk_store(pk + pi, v);
+    pk_store(pk, q, v);
     if (!PLAIN && u.hist) p.hist_params[u.hist_off + pi] = v.th;
   }
 }
@@ -663,23 +684,25 @@ __device__ __forceinline__ void su2_lmul_axis(int a, R c, R s, R& ar, R& ai, R& 
 template <typename R>
 struct GateIn {
   int pi0, pi1, pi2, axes;
+  int q0;                 // position of the first rotation's parameter in the packed state; the others: + 2 TPS each
   Pk4<R> v0, v1, v2;
   R sx, sy, sz, c2, s2, c3, s3;
 };
-template <typename R>
-__device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const UpdCtx<R>& u, const Pk4<R>* pk, bool valid,
+template <typename R, int NQ, int TPS>
+__device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const UpdCtx<R>& u, const R* pk, bool valid, int g,
                                                     const Su2Meta* md, const HSu2* ms, const R* cf, const R* ax) {
   GateIn<R> in;
-  in.pi0 = in.pi1 = in.pi2 = -1; in.axes = 0xfff;
+  in.pi0 = in.pi1 = in.pi2 = -1; in.axes = 0xfff; in.q0 = 0;
   in.v0 = in.v1 = in.v2 = Pk4<R>{R(0), R(0), R(0), R(0)};
   in.sx = in.sy = in.sz = in.c2 = in.s2 = in.c3 = in.s3 = R(0);
   if (!valid) return in;
   const HSu2 hm = *ms;
   in.pi0 = hm.pidx[0]; in.pi1 = hm.pidx[1]; in.pi2 = hm.pidx[2];
   in.axes = hm.axes;
-  if (in.pi0 >= 0) in.v0 = pk_load(pk + in.pi0); else in.v0.th = R(md->cangle[0]);
-  if (in.pi1 >= 0) in.v1 = pk_load(pk + in.pi1); else in.v1.th = R(md->cangle[1]);
-  if (in.pi2 >= 0) in.v2 = pk_load(pk + in.pi2); else in.v2.th = R(md->cangle[2]);
+  in.q0 = heis_pk_pos_su2(g, 0, NQ, TPS);
+  if (in.pi0 >= 0) in.v0 = pk_load(pk, in.q0); else in.v0.th = R(md->cangle[0]);
+  if (in.pi1 >= 0) in.v1 = pk_load(pk, in.q0 + 2 * TPS); else in.v1.th = R(md->cangle[1]);
+  if (in.pi2 >= 0) in.v2 = pk_load(pk, in.q0 + 4 * TPS); else in.v2.th = R(md->cangle[2]);
   if (u.phase != PH_COEF) {
     // gradient sums of the backward sweep, back to the gate's output frame: the sweep reads them after the gate's
     // own Rz(phi_out + pi/2) is undone, e^{i w} = i u_out (u_out is still in words 2, 3 from the last update)
@@ -692,8 +715,8 @@ __device__ __forceinline__ GateIn<R> heis_gate_load(const KParams<R>& p, const U
 
 // Fused one-qubit gate: finish the step (chain rule through the fusion, Adam), then the new ZYZ data of the gate.
 // AX* >= 0: compile-time rotation axes (the selects fold away); AX0 == -2: axes from the gate metadata.
-template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
-__device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, Pk4<R>* pk, const Su2Meta* md,
+template <typename R, int TPS, int AX0, int AX1, int AX2, bool PLAIN>
+__device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCtx<R>& u, R* pk, const Su2Meta* md,
                                                 GateIn<R> in, R* cf, R* ax) {
   const int a0 = in.axes & 15, a1 = (in.axes >> 4) & 15, a2 = (in.axes >> 8) & 15;   // 15 = unused slot
   const int ax0 = AX0 == -2 ? (a0 == 15 ? -1 : a0) : AX0;
@@ -710,9 +733,9 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
     const R g1 = sel3(ax1, sx, sy, sz);
     rot_axis(ax1, C2, -S2, sx, sy, sz);
     const R g0 = sel3(ax0, sx, sy, sz);
-    if (in.pi2 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi2, g2, in.v2);
-    if (in.pi1 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi1, g1, in.v1);
-    if (in.pi0 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi0, g0, in.v0);
+    if (in.pi2 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi2, in.q0 + 4 * TPS, g2, in.v2);
+    if (in.pi1 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi1, in.q0 + 2 * TPS, g1, in.v1);
+    if (in.pi0 >= 0) heis_apply<R, PLAIN>(p, u, pk, in.pi0, in.q0, g0, in.v0);
   }
   if (!u.skip_coef) {
     R c0 = R(1), s0 = R(0), c1 = R(1), s1 = R(0), c2 = R(1), s2 = R(0);
@@ -734,6 +757,222 @@ __device__ __forceinline__ void heis_su2_update(const KParams<R>& p, const UpdCt
     cf[4] = par * pbr - pai * pbi; cf[5] = -(par * pbi + pai * pbr);
   }
 }
+// ------------------------------------------------------------------------------------------
+// Packed update of TWO fused gates per thread (float, PLAIN runs, compile-time axes): component .x is gate g, .y is
+// gate g + stride of the same lane.  The parameter phase is latency bound (dependent FMA / MUFU chains, two warps per
+// scheduler and CTA): two gates side by side in FFMA2 / FMUL2 / FADD2 halve its instruction count and double the
+// work in flight per thread.  Every component follows the arithmetic of the scalar float path operation by operation
+// (same roundings: Adam as separate multiplies and adds), so a gate's result does not depend on its partner.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 p2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 sel2(bool kx, bool ky, float2 a, float2 b) { return make_float2(kx ? a.x : b.x, ky ? a.y : b.y); }
+
+// x' = C x - S y; y' = S x + C y on the two coordinates the axis does not fix (rot_axis, packed)
+template <int A>
+__device__ __forceinline__ void rot_axis2(float2 C, float2 S, float2 nS, float2& x, float2& y, float2& z) {
+  if constexpr (A == 0) { const float2 ny = fma2(nS, z, mul2(C, y)), nz = fma2(S, y, mul2(C, z)); y = ny; z = nz; }
+  else if constexpr (A == 1) { const float2 nz = fma2(nS, x, mul2(C, z)), nx = fma2(S, z, mul2(C, x)); z = nz; x = nx; }
+  else if constexpr (A == 2) { const float2 nx = fma2(nS, y, mul2(C, x)), ny = fma2(S, x, mul2(C, y)); x = nx; y = ny; }
+}
+template <int A> __device__ __forceinline__ float2 sel3c(float2 x, float2 y, float2 z) { return A == 0 ? x : (A == 1 ? y : z); }
+// (alpha, beta) <- R_A(c, s) (alpha, beta)   (su2_lmul_axis, packed)
+template <int A>
+__device__ __forceinline__ void su2_lmul_axis2(float2 c, float2 s, float2& ar, float2& ai, float2& br, float2& bi) {
+  const float2 ns = neg2(s);
+  if constexpr (A == 0) {
+    const float2 nar = fma2(s, bi, mul2(c, ar)), nai = fma2(ns, br, mul2(c, ai)), nbr = fma2(s, ai, mul2(c, br)),
+                 nbi = fma2(ns, ar, mul2(c, bi));
+    ar = nar; ai = nai; br = nbr; bi = nbi;
+  } else if constexpr (A == 1) {
+    const float2 nar = fma2(ns, br, mul2(c, ar)), nai = fma2(ns, bi, mul2(c, ai)), nbr = fma2(s, ar, mul2(c, br)),
+                 nbi = fma2(s, ai, mul2(c, bi));
+    ar = nar; ai = nai; br = nbr; bi = nbi;
+  } else if constexpr (A == 2) {
+    const float2 nar = fma2(s, ai, mul2(c, ar)), nai = fma2(ns, ar, mul2(c, ai)), nbr = fma2(ns, bi, mul2(c, br)),
+                 nbi = fma2(s, br, mul2(c, bi));
+    ar = nar; ai = nai; br = nbr; bi = nbi;
+  }
+}
+// R_A1(c1, s1) R_A0(c0, s0) as (alpha, beta): every component is one product (the zeros of su2_of folded by hand)
+template <int A0, int A1>
+__device__ __forceinline__ void su2_two2(float2 c0, float2 s0, float2 c1, float2 s1, float2& ar, float2& ai, float2& br,
+                                         float2& bi) {
+  const float2 z = bc2(0.f);
+  ar = c0; ai = z; br = z; bi = z;
+  if constexpr (A0 == 0) bi = neg2(s0); else if constexpr (A0 == 1) br = s0; else ai = neg2(s0);
+  su2_lmul_axis2<A1>(c1, s1, ar, ai, br, bi);
+}
+__device__ __forceinline__ float2 rsqrt_fast2(float2 a) {
+  float rx, ry;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(a.x));
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(a.y));
+  const float2 r = p2(rx, ry);
+  const float2 nh = mul2(mul2(bc2(-0.5f), a), r);              // -(0.5 a) r, rounded like the scalar 0.5f * a * r
+  return fma2(r, fma2(nh, r, bc2(0.5f)), r);
+}
+__device__ __forceinline__ float2 rcp_fast2(float2 a) {
+  float rx, ry;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(a.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(a.y));
+  const float2 r = p2(rx, ry);
+  return fma2(r, fma2(neg2(a), r, bc2(1.0f)), r);
+}
+// sincos_core on both components
+__device__ __forceinline__ void sincos_core2(float2 x, float2& s, float2& c) {
+  const float2 t = mul2(x, bc2(0.636619747f));
+  const float2 j = p2(rintf(t.x), rintf(t.y));
+  float2 r = fma2(j, bc2(-1.57079601e+00f), x);
+  r = fma2(j, bc2(-3.13916473e-07f), r);
+  r = fma2(j, bc2(-5.39030253e-15f), r);
+  const int qx = __float2int_rn(j.x), qy = __float2int_rn(j.y);
+  const float2 r2 = mul2(r, r);
+  float2 sp = fma2(r2, bc2(-1.9515295891e-4f), bc2(8.3321608736e-3f));
+  sp = fma2(sp, r2, bc2(-1.6666654611e-1f));
+  sp = fma2(mul2(sp, r2), r, r);
+  float2 cp = fma2(r2, bc2(2.443315711809948e-5f), bc2(-1.388731625493765e-3f));
+  cp = fma2(cp, r2, bc2(4.166664568298827e-2f));
+  cp = fma2(mul2(cp, r2), r2, fma2(r2, bc2(-0.5f), bc2(1.0f)));
+  const float ssx = (qx & 1) ? cp.x : sp.x, ccx = (qx & 1) ? sp.x : cp.x;
+  const float ssy = (qy & 1) ? cp.y : sp.y, ccy = (qy & 1) ? sp.y : cp.y;
+  s = p2((qx & 2) ? -ssx : ssx, (qy & 2) ? -ssy : ssy);
+  c = p2(((qx + 1) & 2) ? -ccx : ccx, ((qy + 1) & 2) ? -ccy : ccy);
+}
+
+// What the update of a gate pair reads from global memory (requested one pair ahead): theta, m, v of the three
+// rotations, .x = gate a, .y = gate b (one aligned 8-byte pair per field in the lane-interleaved state).
+struct PairGlob { float2 th0, mu0, nu0, th1, mu1, nu1, th2, mu2, nu2; };
+template <int TPS>
+__device__ __forceinline__ PairGlob heis_pair_load(const float* pk, int q0, bool valid) {
+  PairGlob q;
+  const float2 z = make_float2(0.f, 0.f);
+  q.th0 = q.mu0 = q.nu0 = q.th1 = q.mu1 = q.nu1 = q.th2 = q.mu2 = q.nu2 = z;
+  if (valid) {
+    const float* b0 = pk_at(pk, q0);
+    const float* b1 = pk_at(pk, q0 + 2 * TPS);
+    const float* b2 = pk_at(pk, q0 + 4 * TPS);
+    q.th0 = *reinterpret_cast<const float2*>(b0); q.mu0 = *reinterpret_cast<const float2*>(b0 + 16);
+    q.nu0 = *reinterpret_cast<const float2*>(b0 + 32);
+    q.th1 = *reinterpret_cast<const float2*>(b1); q.mu1 = *reinterpret_cast<const float2*>(b1 + 16);
+    q.nu1 = *reinterpret_cast<const float2*>(b1 + 32);
+    q.th2 = *reinterpret_cast<const float2*>(b2); q.mu2 = *reinterpret_cast<const float2*>(b2 + 16);
+    q.nu2 = *reinterpret_cast<const float2*>(b2 + 32);
+  }
+  return q;
+}
+// Adam on a parameter pair (adam_inl, float, packed) and the stores of the pair's fields
+__device__ __forceinline__ void heis_apply2(const KParams<float>& p, const UpdCtx<float>& u, float* pk, int q, float2 g,
+                                            float2& th, float2& mu, float2& nu) {
+  float* b = pk_at(pk, q);
+  // th is still the pre-update parameter of the step being finished (optimization.py:70-73)
+  if (u.store_best && u.active) *reinterpret_cast<float2*>(b + 48) = th;
+  mu = add2(mul2(bc2(p.omb1), g), mul2(bc2(p.b1), mu));
+  nu = add2(mul2(bc2(p.omb2), mul2(g, g)), mul2(bc2(p.b2), nu));
+  const float2 mh = mul2(mu, bc2(u.ibc1)), nh = mul2(nu, bc2(u.ibc2));
+  float rx, ry, ix, iy;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(nh.x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(nh.y));
+  const float2 den = add2(p2(rx, ry), bc2(p.eps));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(den.y));
+  th = add2(th, mul2(bc2(-p.lr), mul2(mh, p2(ix, iy))));
+  if (u.active) {
+    *reinterpret_cast<float2*>(b) = th;
+    *reinterpret_cast<float2*>(b + 16) = mu;
+    *reinterpret_cast<float2*>(b + 32) = nu;
+  }
+}
+// ga, gb: the pair's gates (slots); q0: position of rotation 0 of gate a (gate b: q0 + 1); has_b: gate b exists (the
+// fields of a missing gate are zero: heis_kernel zeroes unused positions when it packs the state)
+template <int TPS, int AX0, int AX1, int AX2>
+__device__ __forceinline__ void heis_pair_update(const KParams<float>& p, const UpdCtx<float>& u, float* pk, PairGlob q,
+                                                 int q0, int ga, int gb, bool has_b, float* coef) {
+  constexpr int SW = HEIS_SU2_WORDS;
+  float* cfa = coef + SW * ga;
+  float* cfb = coef + SW * (has_b ? gb : ga);
+  float big = 0.f;
+  if (u.phase != PH_COEF) {
+    // gradient sums of the backward sweep, back to the gates' output frames (heis_gate_load)
+    const float4 la = *reinterpret_cast<const float4*>(cfa), lb = *reinterpret_cast<const float4*>(cfb);
+    const float2 px = p2(la.x, lb.x), py = p2(la.y, lb.y), wi = p2(la.z, lb.z), wr = p2(-la.w, -lb.w);
+    float2 sx = fma2(neg2(wi), py, mul2(wr, px)), sy = fma2(wr, py, mul2(wi, px)), sz = p2(cfa[4], cfb[4]);
+    // half-angle cos / sin of the second and third rotation at the parameters of the step being finished: recomputed
+    // (the scalar path keeps them in global memory: 32 bytes of L2 traffic per gate and step)
+    const float2 y1 = mul2(q.th1, bc2(0.5f)), y2 = mul2(q.th2, bc2(0.5f));
+    float2 c2, s2, c3, s3;
+    sincos_core2(y1, s2, c2); sincos_core2(y2, s3, c3);
+    big = fmaxf(fmaxf(fabsf(y1.x), fabsf(y1.y)), fmaxf(fabsf(y2.x), fabsf(y2.y)));
+    if (big > 48000.f) {
+      sincos_inl(y1.x, s2.x, c2.x); sincos_inl(y1.y, s2.y, c2.y); sincos_inl(y2.x, s3.x, c3.x); sincos_inl(y2.y, s3.y, c3.y);
+    }
+    // chain rule through G = R_2 R_1 R_0 (heis_su2_update); rotations by -theta: (C, -S) with S = 2 c s
+    const float2 C2 = fma2(c2, c2, neg2(mul2(s2, s2))), t2 = mul2(bc2(2.f), c2), S2 = mul2(t2, s2), nS2 = mul2(neg2(t2), s2);
+    const float2 C3 = fma2(c3, c3, neg2(mul2(s3, s3))), t3 = mul2(bc2(2.f), c3), S3 = mul2(t3, s3), nS3 = mul2(neg2(t3), s3);
+    const float2 g2 = sel3c<AX2>(sx, sy, sz);
+    rot_axis2<AX2>(C3, nS3, S3, sx, sy, sz);
+    const float2 g1 = sel3c<AX1>(sx, sy, sz);
+    rot_axis2<AX1>(C2, nS2, S2, sx, sy, sz);
+    const float2 g0 = sel3c<AX0>(sx, sy, sz);
+    heis_apply2(p, u, pk, q0 + 4 * TPS, g2, q.th2, q.mu2, q.nu2);
+    heis_apply2(p, u, pk, q0 + 2 * TPS, g1, q.th1, q.mu1, q.nu1);
+    heis_apply2(p, u, pk, q0, g0, q.th0, q.mu0, q.nu0);
+  }
+  if (!u.skip_coef) {
+    const float2 x0 = mul2(q.th0, bc2(0.5f)), x1 = mul2(q.th1, bc2(0.5f)), x2 = mul2(q.th2, bc2(0.5f));
+    float2 s0, c0, s1, c1, s2, c2;
+    sincos_core2(x0, s0, c0); sincos_core2(x1, s1, c1); sincos_core2(x2, s2, c2);
+    big = fmaxf(fmaxf(fmaxf(fabsf(x0.x), fabsf(x0.y)), fmaxf(fabsf(x1.x), fabsf(x1.y))),
+                fmaxf(fabsf(x2.x), fabsf(x2.y)));
+    if (big > 48000.f) {           // never taken in practice: large-argument reduction out of line
+      sincos_inl(x0.x, s0.x, c0.x); sincos_inl(x0.y, s0.y, c0.y); sincos_inl(x1.x, s1.x, c1.x);
+      sincos_inl(x1.y, s1.y, c1.y); sincos_inl(x2.x, s2.x, c2.x); sincos_inl(x2.y, s2.y, c2.y);
+    }
+    float2 ar, ai, br, bi;
+    su2_two2<AX0, AX1>(c0, s0, c1, s1, ar, ai, br, bi);
+    su2_lmul_axis2<AX2>(c2, s2, ar, ai, br, bi);
+    // ZYZ form for the forward sweep (heis_su2_update)
+    const float2 na = fma2(ar, ar, mul2(ai, ai)), nb = fma2(br, br, mul2(bi, bi));
+    const bool oax = na.x > 1e-30f, oay = na.y > 1e-30f, obx = nb.x > 1e-30f, oby = nb.y > 1e-30f;
+    const float2 zero = bc2(0.f), one = bc2(1.f);
+    const float2 ia = sel2(oax, oay, rsqrt_fast2(na), zero), ib = sel2(obx, oby, rsqrt_fast2(nb), zero);
+    const float2 par = sel2(oax, oay, mul2(ar, ia), one), pai = mul2(ai, ia);
+    const float2 pbr = sel2(obx, oby, mul2(br, ib), one), pbi = mul2(bi, ib);
+    const float2 cyv = mul2(na, ia), syv = mul2(nb, ib);
+    const float2 ty = mul2(neg2(syv), rcp_fast2(add2(one, cyv)));
+    const float2 uor = fma2(pbr, par, mul2(pbi, pai)), uoi = fma2(pbi, par, neg2(mul2(pbr, pai)));
+    const float2 uir = fma2(par, pbr, neg2(mul2(pai, pbi))), uii = neg2(fma2(par, pbi, mul2(pai, pbr)));
+    *reinterpret_cast<float4*>(cfa) = make_float4(ty.x, syv.x, uor.x, uoi.x);
+    *reinterpret_cast<float2*>(cfa + 4) = make_float2(uir.x, uii.x);
+    if (has_b) {
+      *reinterpret_cast<float4*>(cfb) = make_float4(ty.y, syv.y, uor.y, uoi.y);
+      *reinterpret_cast<float2*>(cfb + 4) = make_float2(uir.y, uii.y);
+    }
+  }
+}
+// gates g0, g0 + TPS, ... < g_end of one class, two at a time (g0 is the lane's first gate of the class, so the pair
+// (g, g + TPS) shares one 8-byte slot per field); the state of the next pair is requested before the current pair
+// is processed.
+template <int NQ, int TPS, int AX0, int AX1, int AX2>
+__device__ __forceinline__ void heis_su2_loop_pair(const KParams<float>& p, const UpdCtx<float>& u, float* pk, int g0,
+                                                   int g_end, float* coef) {
+  int q0 = heis_pk_pos_su2(g0, 0, NQ, TPS);
+  PairGlob qa = heis_pair_load<TPS>(pk, q0, g0 < g_end);
+#pragma unroll 1
+  for (int g = g0; g < g_end; g += 4 * TPS) {
+    // consecutive pairs of a lane are 6 TPS positions apart (three rotations x TPS lanes x 2)
+    const PairGlob qb = heis_pair_load<TPS>(pk, q0 + 6 * TPS, g + 2 * TPS < g_end);
+    heis_pair_update<TPS, AX0, AX1, AX2>(p, u, pk, qa, q0, g, g + TPS, g + TPS < g_end, coef);
+    qa = heis_pair_load<TPS>(pk, q0 + 12 * TPS, g + 4 * TPS < g_end);
+    if (g + 2 * TPS < g_end)
+      heis_pair_update<TPS, AX0, AX1, AX2>(p, u, pk, qb, q0 + 6 * TPS, g + 2 * TPS, g + 3 * TPS, g + 3 * TPS < g_end, coef);
+    q0 += 12 * TPS;
+  }
+}
+
 // packed axes of a gate class: a0 | a1 << 4 | a2 << 8 (15 = unused slot); 0xffff = not uniform
 constexpr int AXP_ZXZ = 2 | (0 << 4) | (2 << 8);
 constexpr int AXP_XYZ = 0 | (1 << 4) | (2 << 8);
@@ -742,39 +981,63 @@ constexpr int AXP_XZ = 0 | (2 << 4) | (15 << 8);
 // gates g0, g0 + stride, ... < g_end of one class (compile-time axes), software pipelined.  (Issuing the first loads of
 // all three gate classes together at the top of the parameter phase was measured: no gain in float - 121.6 vs 121.3 M
 // evals/s on C3 - and 1.5 KB of spills in the double kernels; each loop keeps its own prologue.)
-template <typename R, int AX0, int AX1, int AX2, bool PLAIN>
-__device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, Pk4<R>* pk, int g0,
-                                              int g_end, int stride, R* coef, R* aux) {
+template <typename R, int NQ, int TPS, int AX0, int AX1, int AX2, bool PLAIN>
+__device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* ms, const UpdCtx<R>& u, R* pk, int g0,
+                                              int g_end, R* coef, R* aux) {
+  constexpr int stride = TPS;
   constexpr int SW = HEIS_SU2_WORDS;
   // Two gates in flight, loop unrolled by two so that the buffers keep their registers (no copies at the back
   // edge): the state of gate g + 2 stride is requested as soon as gate g is done and has the whole update of
   // gate g + stride to arrive (the L2 round trip is about as long as one gate's update).
-  GateIn<R> ga = heis_gate_load(p, u, pk, g0 < g_end, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
-  GateIn<R> gb = heis_gate_load(p, u, pk, g0 + stride < g_end, p.su2 + g0 + stride, ms + g0 + stride,
-                                coef + SW * (g0 + stride), aux + 4 * (g0 + stride));
+  GateIn<R> ga = heis_gate_load<R, NQ, TPS>(p, u, pk, g0 < g_end, g0, p.su2 + g0, ms + g0, coef + SW * g0, aux + 4 * g0);
+  GateIn<R> gb = heis_gate_load<R, NQ, TPS>(p, u, pk, g0 + stride < g_end, g0 + stride, p.su2 + g0 + stride, ms + g0 + stride,
+                                            coef + SW * (g0 + stride), aux + 4 * (g0 + stride));
 #pragma unroll 1
   for (int g = g0; g < g_end; g += 2 * stride) {
-    heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, ga, coef + SW * g, aux + 4 * g);
+    heis_su2_update<R, TPS, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g, ga, coef + SW * g, aux + 4 * g);
     const int g2 = g + 2 * stride;
-    ga = heis_gate_load(p, u, pk, g2 < g_end, p.su2 + g2, ms + g2, coef + SW * g2, aux + 4 * g2);
+    ga = heis_gate_load<R, NQ, TPS>(p, u, pk, g2 < g_end, g2, p.su2 + g2, ms + g2, coef + SW * g2, aux + 4 * g2);
     const int g1 = g + stride;
-    if (g1 < g_end) heis_su2_update<R, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g1, gb, coef + SW * g1, aux + 4 * g1);
+    if (g1 < g_end) heis_su2_update<R, TPS, AX0, AX1, AX2, PLAIN>(p, u, pk, p.su2 + g1, gb, coef + SW * g1, aux + 4 * g1);
     const int g3 = g + 3 * stride;
-    gb = heis_gate_load(p, u, pk, g3 < g_end, p.su2 + g3, ms + g3, coef + SW * g3, aux + 4 * g3);
+    gb = heis_gate_load<R, NQ, TPS>(p, u, pk, g3 < g_end, g3, p.su2 + g3, ms + g3, coef + SW * g3, aux + 4 * g3);
   }
 }
-template <typename R>
+template <typename R, int NQ, int TPS>
 __device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const HSu2* ms,
-                                                  const UpdCtx<R>& u, Pk4<R>* pk, int g0, int g_end, int stride, R* coef,
-                                                  R* aux) {
+                                                  const UpdCtx<R>& u, R* pk, int g0, int g_end, R* coef, R* aux) {
+  if constexpr (sizeof(R) == 4) {
+    // float Adam runs without freeze mask / history whose fused gates are all-parameter: two gates per thread, packed
+    if (plain && p.su2_all_params) {
+      if (axp == AXP_XYZ) { heis_su2_loop_pair<NQ, TPS, 0, 1, 2>(p, u, pk, g0, g_end, coef); return; }
+      if (axp == AXP_ZXZ) { heis_su2_loop_pair<NQ, TPS, 2, 0, 2>(p, u, pk, g0, g_end, coef); return; }
+    }
+  }
   if (axp == AXP_XYZ) {
-    if (plain) heis_su2_loop<R, 0, 1, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-    else heis_su2_loop<R, 0, 1, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    if (plain) heis_su2_loop<R, NQ, TPS, 0, 1, 2, true>(p, ms, u, pk, g0, g_end, coef, aux);
+    else heis_su2_loop<R, NQ, TPS, 0, 1, 2, false>(p, ms, u, pk, g0, g_end, coef, aux);
   } else if (axp == AXP_ZXZ) {
-    if (plain) heis_su2_loop<R, 2, 0, 2, true>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-    else heis_su2_loop<R, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-  } else if (axp == AXP_XZ) heis_su2_loop<R, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
-  else heis_su2_loop<R, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, stride, coef, aux);
+    if (plain) heis_su2_loop<R, NQ, TPS, 2, 0, 2, true>(p, ms, u, pk, g0, g_end, coef, aux);
+    else heis_su2_loop<R, NQ, TPS, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, coef, aux);
+  } else if (axp == AXP_XZ) heis_su2_loop<R, NQ, TPS, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, coef, aux);
+  else heis_su2_loop<R, NQ, TPS, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, coef, aux);
+}
+
+// f(parameter index or -1, position) for every position of the packed state that lane m of a sample owns: the slots of
+// its fused gates in both update loops (present or not) and its entanglers
+template <int NQ, int TPS, typename F>
+__device__ __forceinline__ void heis_pk_visit(int n_su2, int n_cp, const HSu2* s_su2, const HCp* s_cp, int m, F f) {
+  for (int j = 0; j < 3; ++j) {
+    const int q = (j * TPS + m) * 2;
+    f(m < NQ && m < n_su2 ? (int)s_su2[m].pidx[j] : -1, q);
+    f(-1, q + 1);
+  }
+  const int iters = 2 * heis_pk_pair_iters(NQ, TPS, n_su2);
+  for (int i = 0; i < iters; ++i) {
+    const int g = NQ + m + i * TPS;
+    for (int j = 0; j < 3; ++j) f(g < n_su2 ? (int)s_su2[g].pidx[j] : -1, heis_pk_pos_su2(g, j, NQ, TPS));
+  }
+  for (int k = m; k < n_cp; k += TPS) f((int)s_cp[k].pidx, heis_pk_cp_base(NQ, TPS, n_su2) + k);
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -847,18 +1110,23 @@ heis_kernel(const KParams<R> p) {
 
   const unsigned off = (unsigned)(b * P);   // host: B * P < 2^32
   R* aux = p.aux + (size_t)b * p.n_su2 * 4;
-  Pk4<R>* pk = reinterpret_cast<Pk4<R>*>(p.pk) + off;
+  R* pk = reinterpret_cast<R*>(p.pk) + (size_t)b * p.pk_stride;
+  const int cp_base = heis_pk_cp_base(NQ, TPS, p.n_su2);
   {
-    // pack this sample's optimiser state (a resumed run, step0 > 0, carries its moments and best parameters)
+    // pack this sample's optimiser state (a resumed run, step0 > 0, carries its moments and best parameters);
+    // positions no gate owns are zeroed (the pair path computes on them)
     const bool resume = p.mode == M_ADAM && step0 > 0;
-    for (int i = m; i < P; i += TPS) {
-      Pk4<R> v;
-      v.th = p.angles[off + i];
-      v.mu = resume ? p.m[off + i] : R(0);
-      v.nu = resume ? p.v[off + i] : R(0);
-      v.best = resume ? p.best_params[off + i] : v.th;
-      if (active) pk_store(pk + i, v);
-    }
+    heis_pk_visit<NQ, TPS>(p.n_su2, p.n_cp, s_su2, s_cp, m, [&](int pi, int q) {
+      R th = R(0), mu = R(0), nu = R(0), be = R(0);
+      if (pi >= 0) {
+        th = p.angles[off + pi]; be = th;
+        if (resume) { mu = p.m[off + pi]; nu = p.v[off + pi]; be = p.best_params[off + pi]; }
+      }
+      if (active) { R* d = pk_at(pk, q); d[0] = th; d[16] = mu; d[32] = nu; d[48] = be; }
+    });
+    // parameters that feed no gate never reach the packed state: their outputs are written here
+    if (p.unreferenced_params && p.mode == M_ADAM && !resume && active)
+      for (int i = m; i < P; i += TPS) { p.m[off + i] = R(0); p.v[off + i] = R(0); p.best_params[off + i] = p.angles[off + i]; }
     __syncwarp();
   }
   const R NN = R(N) * R(N);
@@ -875,6 +1143,9 @@ heis_kernel(const KParams<R> p) {
     const int phase = it == 0 ? PH_COEF : (p.mode == M_ADAM ? PH_ADAM : PH_GRAD);
     // ---------------- parameter phase (a sample's threads split the gates) ----------------
     R reg_part = R(0);
+#ifdef CPF_EXP_SKIP_UPDATE      // timing experiment only (tools/build_variant.py): sweeps without the parameter phase
+    if (it == 0 || it == p.nsteps)
+#endif
     {
       UpdCtx<R> u;
       u.phase = phase; u.active = active; u.off = off;
@@ -895,8 +1166,8 @@ heis_kernel(const KParams<R> p) {
       // split and time-sliced runs are bit-identical to one launch by construction, not by the compiler's choice of
       // identical FMA contractions in two instantiations
       const bool plain = p.mode == M_ADAM && p.freeze == nullptr && p.hist_params == nullptr;
-      heis_su2_loop_any(p.axp_surface, plain, p, s_su2, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, TPS, coef, aux);
-      heis_su2_loop_any(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, TPS, coef, aux);
+      heis_su2_loop_any<R, NQ, TPS>(p.axp_surface, plain, p, s_su2, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, coef, aux);
+      heis_su2_loop_any<R, NQ, TPS>(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, coef, aux);
       // entangler angles, software pipelined like the fused-gate loops: the packed state of the next gate is
       // requested before the current one is processed
       {
@@ -904,7 +1175,7 @@ heis_kernel(const KParams<R> p) {
         int pi_n = -1;
         Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
         HCp md_n = HCp{-1, 0, 0, 0};
-        if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
+        if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk, cp_base + k); }
 #pragma unroll 1
         for (; k < p.n_cp; k += TPS) {
           const HCp md = md_n;
@@ -912,15 +1183,15 @@ heis_kernel(const KParams<R> p) {
           const int pi = pi_n;
           Pk4<R> v = v_n;
           const int kn = k + TPS;
-          if (kn < p.n_cp) { md_n = s_cp[kn]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk + pi_n); }
+          if (kn < p.n_cp) { md_n = s_cp[kn]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk, cp_base + kn); }
           const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 && (md.flags & 1) != 0;
           if (pi < 0) v.th = R(p.cp[k].cangle);
           // cf[0]: dL/da from the sweep; word 6 of the block's higher-qubit gate slot: r * penalty slope at this angle
           R* rsw = coef + SW * (NQ + 2 * k + 1) + 6;
           if (phase != PH_COEF && pi >= 0) {
             const R g = add_rn(cf[0], *rsw);
-            if (plain) heis_apply<R, true>(p, u, pk, pi, g, v);
-            else heis_apply<R, false>(p, u, pk, pi, g, v);
+            if (plain) heis_apply<R, true>(p, u, pk, pi, cp_base + k, g, v);
+            else heis_apply<R, false>(p, u, pk, pi, cp_base + k, g, v);
           }
           const R th = v.th;
           if (!u.skip_coef) {
@@ -961,6 +1232,9 @@ heis_kernel(const KParams<R> p) {
     }
     __syncwarp();
 
+#ifdef CPF_EXP_SKIP_SWEEPS      // timing experiment only: parameter phase without the sweeps
+    if (it > 0) { improved_prev = true; continue; }
+#endif
     // ---------------- forward sweep: Y = U V^dag ----------------
     V yr[N], yi[N];
 #pragma unroll
@@ -1027,10 +1301,12 @@ heis_kernel(const KParams<R> p) {
 
   if (p.mode == M_ADAM && active) {
     // unpack the optimiser state into the caller's arrays
-    for (int i = m; i < P; i += TPS) {
-      const Pk4<R> v = pk_load(pk + i);
-      p.angles[off + i] = v.th; p.m[off + i] = v.mu; p.v[off + i] = v.nu; p.best_params[off + i] = v.best;
-    }
+    // (every lane reads back the positions it wrote itself)
+    heis_pk_visit<NQ, TPS>(p.n_su2, p.n_cp, s_su2, s_cp, m, [&](int pi, int q) {
+      if (pi < 0) return;
+      const R* d = pk_at(pk, q);
+      p.angles[off + pi] = d[0]; p.m[off + pi] = d[16]; p.v[off + pi] = d[32]; p.best_params[off + pi] = d[48];
+    });
     if (m == 0) { p.best_regloss[b] = best; p.best_reg[b] = best_reg_v; }
   }
 }
