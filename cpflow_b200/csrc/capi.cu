@@ -148,9 +148,16 @@ int fill_penalty(const cpf::Program* prog, const cpf_penalty_spec* pen, cpf::KPa
     return fail(CPF_ERR_INVALID, "penalty period must be positive");
   p.pen.kind = pen->kind; p.pen.nseg = pen->n_segments;
   p.pen.r = (R)pen->r; p.pen.period = (R)pen->period;
-  for (int s = 0; s < pen->n_segments && s < CPF_MAX_SEGMENTS; ++s) {
-    p.pen.lo[s] = (R)pen->lo[s]; p.pen.hi[s] = (R)pen->hi[s];
-    p.pen.slope[s] = (R)pen->slope[s]; p.pen.icpt[s] = (R)pen->intercept[s];
+  for (int s = 0; s < CPF_MAX_SEGMENTS; ++s) {
+    const bool on = pen->kind == CPF_PEN_PIECEWISE && s < pen->n_segments;
+    p.pen.lo[s] = on ? (R)pen->lo[s] : (R)INFINITY; p.pen.hi[s] = on ? (R)pen->hi[s] : (R)INFINITY;
+    p.pen.slope[s] = on ? (R)pen->slope[s] : R(0); p.pen.icpt[s] = on ? (R)pen->intercept[s] : R(0);
+  }
+  // ascending, disjoint segments (in the kernel's precision) can be searched instead of scanned
+  p.pen.sorted = pen->kind == CPF_PEN_PIECEWISE;
+  for (int s = 0; s < pen->n_segments && s < CPF_MAX_SEGMENTS && p.pen.sorted; ++s) {
+    if (!(p.pen.lo[s] <= p.pen.hi[s])) p.pen.sorted = 0;
+    if (s + 1 < pen->n_segments && !(p.pen.hi[s] <= p.pen.lo[s + 1])) p.pen.sorted = 0;
   }
   if (pen->cp_mask) {
     // only parameters of CP gates may be penalised
@@ -286,7 +293,11 @@ int stage_heis(const cpf::Program* prog, const cpf_loss_spec* loss, cpf::KParams
       if (md.axis[k] >= 0 && md.pidx[k] < 0) p.su2_all_params = 0;
       if (md.pidx[k] >= 0) ++referenced;
     }
-  for (const cpf::CpMeta& md : prog->cp) if (md.pidx >= 0) ++referenced;
+  p.cp_all_params = 1;
+  for (const cpf::CpMeta& md : prog->cp) {
+    if (md.pidx >= 0) ++referenced;
+    if (md.pidx < 0 || md.is_cz) p.cp_all_params = 0;
+  }
   p.unreferenced_params = referenced != prog->n_params;      // (a parameter feeds at most one gate: program.cpp)
   p.pk_stride = cpf::heis_pk_stride(prog->n_qubits, (1 << prog->n_qubits) / cpt, (int)prog->su2.size(), (int)prog->cp.size());
   return CPF_OK;

@@ -37,6 +37,7 @@ enum Mode : int { M_ADAM = 0, M_LOSSGRAD = 1, M_UNITARY = 2, M_COTANGENT = 3 };
 template <typename R>
 struct PenaltyT {
   int kind, nseg;
+  int sorted;   // segments ascending and disjoint (hi[s] <= lo[s + 1]; slots >= nseg hold +inf): binary search allowed
   R r, period;
   R lo[CPF_MAX_SEGMENTS], hi[CPF_MAX_SEGMENTS], slope[CPF_MAX_SEGMENTS], icpt[CPF_MAX_SEGMENTS];
 };
@@ -71,6 +72,7 @@ struct KParams {
   int axp_surface, axp_block;   // heis_kernel: packed rotation axes shared by the surface / block gates
   int su2_all_params;           // heis_kernel: every rotation of every fused gate is a parameter (no constant angles)
   int unreferenced_params;      // heis_kernel: some parameters feed no gate
+  int cp_all_params;            // heis_kernel: every entangler is a CP gate with a parameter (no CZ, no constant angle)
   int pk_stride;                // heis_kernel: words of R per sample in the packed optimiser state (heis_pk_stride)
   int last_slot[8];             // heis_kernel: slot of the last fused gate on each qubit
   PenaltyT<R> pen;
@@ -230,12 +232,24 @@ __device__ __forceinline__ void penalty_eval_fast(const PenaltyT<R>& pen, R a, R
     else am = pymod(a, per);
     R sl = R(0), ic = R(0);
     bool found = false;
+    if (pen.sorted) {
+      // ascending disjoint segments (every table penalty.py builds): at most one matches, branch-free lower bound
+      // over hi[] (16 slots, the unused ones +inf)
+      static_assert(CPF_MAX_SEGMENTS == 16, "lower bound below is written for 16 slots");
+      int s = pen.hi[7] < am ? 8 : 0;
+      s += pen.hi[s + 3] < am ? 4 : 0;
+      s += pen.hi[s + 1] < am ? 2 : 0;
+      s += pen.hi[s] < am ? 1 : 0;
+      found = pen.lo[s] < am && am <= pen.hi[s];
+      sl = pen.slope[s]; ic = pen.icpt[s];
+    } else {
 #pragma unroll
-    for (int s = CPF_MAX_SEGMENTS - 1; s >= 0; --s) {
-      const bool in = s < pen.nseg && pen.lo[s] < am && am <= pen.hi[s];
-      sl = in ? pen.slope[s] : sl;
-      ic = in ? pen.icpt[s] : ic;
-      found = found || in;
+      for (int s = CPF_MAX_SEGMENTS - 1; s >= 0; --s) {
+        const bool in = s < pen.nseg && pen.lo[s] < am && am <= pen.hi[s];
+        sl = in ? pen.slope[s] : sl;
+        ic = in ? pen.icpt[s] : ic;
+        found = found || in;
+      }
     }
     if (found) { val = add_rn(mul_rn(sl, am), ic); slope = sl; }
   } else if (pen.kind == CPF_PEN_L1) {

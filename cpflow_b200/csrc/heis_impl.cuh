@@ -241,13 +241,18 @@ struct HeisSweep {
       // x bit = xr: I = h[0][z], Z = h[0][z|1], X = h[1][z], Y = h[1][z|1]
       R ct, st, cz, sz;
       Vec4Load<R>::ld(cf + 4, ct, st, cz, sz);
+      // Rx mixes the two halves of hv[z | BM] = (Z, Y): one packed multiply-add with the swapped register
+      // ((Z', Y') = ct (Z, Y) + (-st, st) (Y, Z)); every FP instruction, packed or scalar, costs the same issue time
+      // next to packed ones (tools/issue_mix.cu), so 2 packed + 4 scalar beat 8 scalar
+      const V kct = T::bc(ct), kms = T::make(-st, st);
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & BM) continue;
-        const R X = T::get(hv[z], 1), Y = T::get(hv[z | BM], 1), Z = T::get(hv[z | BM], 0);
-        const R Y1 = ct * Y + st * Z;
+        const V h1 = hv[z | BM];
+        const V n1 = T::fma(kms, T::make(T::get(h1, 1), T::get(h1, 0)), T::mul(kct, h1));
+        const R X = T::get(hv[z], 1), Y1 = T::get(n1, 1);
         hv[z] = T::make(T::get(hv[z], 0), cz * X + sz * Y1);
-        hv[z | BM] = T::make(ct * Z - st * Y, cz * Y1 - sz * X);
+        hv[z | BM] = T::make(T::get(n1, 0), cz * Y1 - sz * X);
       }
     } else {
       // x bit is lane bit J: lanes with the bit clear hold (I, Z), lanes with it set hold (X, Y)
@@ -334,18 +339,20 @@ struct HeisSweep {
       // one of the bits is amplitude bit 0, whose x bit is the packed component xr: scalar per component
       constexpr int BL = B1 >= PB ? B1 : B2;          // the lane bit
       const bool xl = xlane<BL>(m);
+      // packed over xr with per-component coefficients (the two components differ in x1 or x2)
+      R tl[XR], sl[XR], t2[XR], s2[XR];
 #pragma unroll
       for (int xr = 0; xr < XR; ++xr) {
         const bool x1 = B1 >= PB ? xl : xr != 0, x2 = B2 >= PB ? xl : xr != 0, on = x1 != x2;
-        const R tl = on ? t : R(0), sl = on ? s : R(0), t2 = on ? (x1 ? t : -t) : R(0), s2 = on ? (x1 ? s : -s) : R(0);
+        tl[xr] = on ? t : R(0); sl[xr] = on ? s : R(0);
+        t2[xr] = on ? (x1 ? t : -t) : R(0); s2[xr] = on ? (x1 ? s : -s) : R(0);
+      }
+      const V vtl = T::make(tl[0], tl[XR - 1]), vsl = T::make(sl[0], sl[XR - 1]);
+      const V vt2 = T::make(t2[0], t2[XR - 1]), vs2 = T::make(s2[0], s2[XR - 1]);
 #pragma unroll
-        for (int z = 0; z < N; ++z) {
-          if (z & (M1 | M2)) continue;
-          R e00 = T::get(hv[z], xr), e01 = T::get(hv[z | M2], xr), e10 = T::get(hv[z | M1], xr),
-            e11 = T::get(hv[z | M1 | M2], xr);
-          zz_quad<R>(e00, e01, e10, e11, tl, sl, t2, s2);
-          setc(hv[z], xr, e00); setc(hv[z | M2], xr, e01); setc(hv[z | M1], xr, e10); setc(hv[z | M1 | M2], xr, e11);
-        }
+      for (int z = 0; z < N; ++z) {
+        if (z & (M1 | M2)) continue;
+        zz_quad<V>(hv[z], hv[z | M2], hv[z | M1], hv[z | M1 | M2], vtl, vsl, vt2, vs2);
       }
     }
   }
@@ -529,8 +536,8 @@ struct UpdCtx {
 //   surface gates (g < n):      q = (j TPS + g) 2                                  (lane g, one gate per lane)
 //   block gates (gb = g - n):   q = 6 TPS + (((i >> 1) 3 + j) TPS + m) 2 + (i & 1),  m = gb % TPS, i = gb / TPS
 // i.e. the two gates (i even, i odd) a lane updates side by side (heis_pair_update) are the two halves of an aligned
-// 8-byte pair and the 8 lanes of a 4-qubit sample read one contiguous 64-byte row per field.  Entangler k follows at
-// cp_base + k.  The kernel packs the caller's separate arrays (include/cpflow_b200.h: cpf_adam_buffers) into this
+// 8-byte pair and the 8 lanes of a 4-qubit sample read one contiguous 64-byte row per field.  The entanglers follow
+// at cp_base in the same pair-interleaved order (heis_pk_pos_cp).  The kernel packs the caller's separate arrays (include/cpflow_b200.h: cpf_adam_buffers) into this
 // scratch at launch and unpacks at the end; `best` is only ever written (when a step improved), never read back
 // before the unpack.
 __host__ __device__ inline int heis_pk_pos_su2(int g, int j, int nq, int tps) {
@@ -545,9 +552,15 @@ __host__ __device__ inline int heis_pk_pair_iters(int nq, int tps, int n_su2) {
 __host__ __device__ inline int heis_pk_cp_base(int nq, int tps, int n_su2) {
   return 6 * tps + heis_pk_pair_iters(nq, tps, n_su2) * 6 * tps;
 }
+// entangler k = m + TPS i (lane m, i-th entangler of the lane): pairs (i even, i odd) side by side like the fused gates
+__host__ __device__ inline int heis_pk_pos_cp(int k, int cp_base, int tps) {
+  const int m = k % tps, i = k / tps;
+  return cp_base + ((i >> 1) * tps + m) * 2 + (i & 1);
+}
+__host__ __device__ inline int heis_pk_cp_pair_iters(int tps, int n_cp) { return (n_cp + 2 * tps - 1) / (2 * tps); }
 // words (of R) per sample
 __host__ __device__ inline int heis_pk_stride(int nq, int tps, int n_su2, int n_cp) {
-  return ((heis_pk_cp_base(nq, tps, n_su2) + n_cp + 15) & ~15) * 4;
+  return ((heis_pk_cp_base(nq, tps, n_su2) + heis_pk_cp_pair_iters(tps, n_cp) * 2 * tps + 15) & ~15) * 4;
 }
 template <typename R> struct Pk4 { R th, mu, nu, best; };
 template <typename R> __device__ __forceinline__ R* pk_at(R* pk, int q) { return pk + ((q >> 4) << 6) + (q & 15); }
@@ -1003,6 +1016,71 @@ __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* m
     gb = heis_gate_load<R, NQ, TPS>(p, u, pk, g3 < g_end, g3, p.su2 + g3, ms + g3, coef + SW * g3, aux + 4 * g3);
   }
 }
+// Entanglers two at a time (float, PLAIN runs, every entangler a CP gate with a parameter): .x is entangler k, .y is
+// k + TPS; same arithmetic per component as the scalar loop in heis_kernel.
+template <int NQ, int TPS>
+__device__ __forceinline__ void heis_cp_loop_pair(const KParams<float>& p, const UpdCtx<float>& u, const HCp* s_cp, float* pk,
+                                                  int cp_base, int m, float* coef, float* coef_cp, float& reg_part) {
+  constexpr int SW = HEIS_SU2_WORDS, CW = HEIS_CP_WORDS;
+  const float2 z = make_float2(0.f, 0.f);
+  int q = cp_base + 2 * m;
+  float2 th_n = z, mu_n = z, nu_n = z;
+  if (m < p.n_cp) {
+    const float* b = pk_at(pk, q);
+    th_n = *reinterpret_cast<const float2*>(b); mu_n = *reinterpret_cast<const float2*>(b + 16);
+    nu_n = *reinterpret_cast<const float2*>(b + 32);
+  }
+#pragma unroll 1
+  for (int k = m; k < p.n_cp; k += 2 * TPS) {
+    float2 th = th_n, mu = mu_n, nu = nu_n;
+    const int kb = k + TPS, kn = k + 2 * TPS;
+    const bool has_b = kb < p.n_cp;
+    if (kn < p.n_cp) {
+      const float* b = pk_at(pk, q + 2 * TPS);
+      th_n = *reinterpret_cast<const float2*>(b); mu_n = *reinterpret_cast<const float2*>(b + 16);
+      nu_n = *reinterpret_cast<const float2*>(b + 32);
+    }
+    const bool pen_a = p.pen.kind != CPF_PEN_NONE && (s_cp[k].flags & 1) != 0;
+    const bool pen_b = p.pen.kind != CPF_PEN_NONE && has_b && (s_cp[has_b ? kb : k].flags & 1) != 0;
+    float* cfa = coef_cp + CW * k;
+    float* cfb = coef_cp + CW * (has_b ? kb : k);
+    // word 6 of the block's higher-qubit gate slot: r * penalty slope at this angle
+    float* rsa = coef + SW * (NQ + 2 * k + 1) + 6;
+    float* rsb = coef + SW * (NQ + 2 * (has_b ? kb : k) + 1) + 6;
+    if (u.phase != PH_COEF) {
+      const float2 g = add2(p2(cfa[0], cfb[0]), p2(*rsa, *rsb));
+      heis_apply2(p, u, pk, q, g, th, mu, nu);
+    }
+    if (!u.skip_coef) {
+      const float2 x = mul2(th, bc2(0.5f));
+      float2 s, c;
+      sincos_core2(x, s, c);
+      if (fmaxf(fabsf(x.x), fabsf(x.y)) > 48000.f) { sincos_inl(x.x, s.x, c.x); sincos_inl(x.y, s.y, c.y); }
+      float rs_a = 0.f, rs_b = 0.f;
+      if (pen_a) {
+        float val, slope;
+        penalty_eval_fast(p.pen, th.x, val, slope);
+        reg_part += val;
+        rs_a = mul_rn(p.pen.r, slope);
+      }
+      if (pen_b) {
+        float val, slope;
+        penalty_eval_fast(p.pen, th.y, val, slope);
+        reg_part += val;
+        rs_b = mul_rn(p.pen.r, slope);
+      }
+      // CP(a) = CP(a - 2 pi): keep cos(a/2) >= 0 (phase_bwd)
+      const bool na = c.x < 0.f, nb = c.y < 0.f;
+      c = p2(na ? -c.x : c.x, nb ? -c.y : c.y);
+      s = p2(na ? -s.x : s.x, nb ? -s.y : s.y);
+      const float2 t = mul2(neg2(s), rcp_fast2(add2(bc2(1.f), c)));
+      cfa[0] = c.x; cfa[1] = s.x; cfa[2] = t.x; *rsa = rs_a;
+      if (has_b) { cfb[0] = c.y; cfb[1] = s.y; cfb[2] = t.y; *rsb = rs_b; }
+    }
+    q += 2 * TPS;
+  }
+}
+
 template <typename R, int NQ, int TPS>
 __device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const HSu2* ms,
                                                   const UpdCtx<R>& u, R* pk, int g0, int g_end, R* coef, R* aux) {
@@ -1037,7 +1115,11 @@ __device__ __forceinline__ void heis_pk_visit(int n_su2, int n_cp, const HSu2* s
     const int g = NQ + m + i * TPS;
     for (int j = 0; j < 3; ++j) f(g < n_su2 ? (int)s_su2[g].pidx[j] : -1, heis_pk_pos_su2(g, j, NQ, TPS));
   }
-  for (int k = m; k < n_cp; k += TPS) f((int)s_cp[k].pidx, heis_pk_cp_base(NQ, TPS, n_su2) + k);
+  const int cp_base = heis_pk_cp_base(NQ, TPS, n_su2), cp_iters = 2 * heis_pk_cp_pair_iters(TPS, n_cp);
+  for (int i = 0; i < cp_iters; ++i) {
+    const int k = m + i * TPS;
+    f(k < n_cp ? (int)s_cp[k].pidx : -1, heis_pk_pos_cp(k, cp_base, TPS));
+  }
 }
 
 // The block size is a launch parameter (a multiple of 32 up to HCfg::MAXT); p.spb of its blockDim.x / TPS
@@ -1170,12 +1252,19 @@ heis_kernel(const KParams<R> p) {
       heis_su2_loop_any<R, NQ, TPS>(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, coef, aux);
       // entangler angles, software pipelined like the fused-gate loops: the packed state of the next gate is
       // requested before the current one is processed
-      {
+      bool cp_done = false;
+      if constexpr (sizeof(R) == 4) {
+        if (plain && p.cp_all_params) {
+          heis_cp_loop_pair<NQ, TPS>(p, u, s_cp, pk, cp_base, m, coef, coef_cp, reg_part);
+          cp_done = true;
+        }
+      }
+      if (!cp_done) {
         int k = m;
         int pi_n = -1;
         Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
         HCp md_n = HCp{-1, 0, 0, 0};
-        if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk, cp_base + k); }
+        if (k < p.n_cp) { md_n = s_cp[k]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk, heis_pk_pos_cp(k, cp_base, TPS)); }
 #pragma unroll 1
         for (; k < p.n_cp; k += TPS) {
           const HCp md = md_n;
@@ -1183,15 +1272,15 @@ heis_kernel(const KParams<R> p) {
           const int pi = pi_n;
           Pk4<R> v = v_n;
           const int kn = k + TPS;
-          if (kn < p.n_cp) { md_n = s_cp[kn]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk, cp_base + kn); }
+          if (kn < p.n_cp) { md_n = s_cp[kn]; pi_n = md_n.pidx; if (pi_n >= 0) v_n = pk_load(pk, heis_pk_pos_cp(kn, cp_base, TPS)); }
           const bool pen_on = p.pen.kind != CPF_PEN_NONE && pi >= 0 && (md.flags & 1) != 0;
           if (pi < 0) v.th = R(p.cp[k].cangle);
           // cf[0]: dL/da from the sweep; word 6 of the block's higher-qubit gate slot: r * penalty slope at this angle
           R* rsw = coef + SW * (NQ + 2 * k + 1) + 6;
           if (phase != PH_COEF && pi >= 0) {
             const R g = add_rn(cf[0], *rsw);
-            if (plain) heis_apply<R, true>(p, u, pk, pi, cp_base + k, g, v);
-            else heis_apply<R, false>(p, u, pk, pi, cp_base + k, g, v);
+            if (plain) heis_apply<R, true>(p, u, pk, pi, heis_pk_pos_cp(k, cp_base, TPS), g, v);
+            else heis_apply<R, false>(p, u, pk, pi, heis_pk_pos_cp(k, cp_base, TPS), g, v);
           }
           const R th = v.th;
           if (!u.skip_coef) {
@@ -1389,6 +1478,8 @@ inline HeisGeometry heis_geometry(long long B, size_t fixed_bytes, size_t per_sa
   g.block = (int)((spb * tps + 31) / 32 * 32);
   g.grid = (B + spb - 1) / spb;
   g.smem = fixed_bytes + (size_t)(spb + (g.block > spb * tps ? 1 : 0)) * per_sample;
+  // CPF_HEIS_SOLO=1 (measurements): pad the request so that the hardware cannot co-schedule a second CTA on the SM
+  if (const char* e = getenv("CPF_HEIS_SOLO")) if (e[0] == '1' && g.smem < 120 * 1024) g.smem = 120 * 1024;
   return g;
 }
 

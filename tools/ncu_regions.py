@@ -94,7 +94,7 @@ P(f"{'phase':24s} {'static':>7s} {'instr/eval':>10s} {'%instr':>7s} {'%samples':
 for _, name in marks:
     if name not in agg: continue
     a = agg[name]
-    top = ", ".join(f"{o} {c / evals:.0f}" for o, c in ops[name].most_common(6))
+    top = ", ".join(f"{o} {c / evals:.0f}" for o, c in ops[name].most_common(int(os.environ.get("NCU_REGIONS_TOP", "6"))))
     P(f"{name:24s} {a[3]:7d} {a[0] / evals:10.1f} {100 * a[0] / ti:6.1f}% {100 * a[1] / ts:8.1f}% {1 - a[2] / max(a[1], 1):13.2f}   {top}")
 P(f"total instr/eval {ti / evals:.1f}")
 P("-- stall samples per phase (% of the phase's samples; 'selected' = issuing) --")
