@@ -877,12 +877,13 @@ __device__ __forceinline__ PairGlob heis_pair_load(const float* pk, int q0, bool
   }
   return q;
 }
-// Adam on a parameter pair (adam_inl, float, packed) and the stores of the pair's fields
-__device__ __forceinline__ void heis_apply2(const KParams<float>& p, const UpdCtx<float>& u, float* pk, int q, float2 g,
-                                            float2& th, float2& mu, float2& nu) {
+// Adam on a parameter pair (adam_inl, float, packed) and the stores of the pair's fields (on: the pair exists and the
+// sample is a real one)
+__device__ __forceinline__ void heis_apply2(const KParams<float>& p, const UpdCtx<float>& u, float* pk, int q, bool on,
+                                            float2 g, float2& th, float2& mu, float2& nu) {
   float* b = pk_at(pk, q);
   // th is still the pre-update parameter of the step being finished (optimization.py:70-73)
-  if (u.store_best && u.active) *reinterpret_cast<float2*>(b + 48) = th;
+  if (u.store_best && on) *reinterpret_cast<float2*>(b + 48) = th;
   mu = add2(mul2(bc2(p.omb1), g), mul2(bc2(p.b1), mu));
   nu = add2(mul2(bc2(p.omb2), mul2(g, g)), mul2(bc2(p.b2), nu));
   const float2 mh = mul2(mu, bc2(u.ibc1)), nh = mul2(nu, bc2(u.ibc2));
@@ -893,97 +894,114 @@ __device__ __forceinline__ void heis_apply2(const KParams<float>& p, const UpdCt
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(den.x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(den.y));
   th = add2(th, mul2(bc2(-p.lr), mul2(mh, p2(ix, iy))));
-  if (u.active) {
+  if (on) {
     *reinterpret_cast<float2*>(b) = th;
     *reinterpret_cast<float2*>(b + 16) = mu;
     *reinterpret_cast<float2*>(b + 32) = nu;
   }
 }
-// ga, gb: the pair's gates (slots); q0: position of rotation 0 of gate a (gate b: q0 + 1); has_b: gate b exists (the
-// fields of a missing gate are zero: heis_kernel zeroes unused positions when it packs the state)
-template <int TPS, int AX0, int AX1, int AX2>
-__device__ __forceinline__ void heis_pair_update(const KParams<float>& p, const UpdCtx<float>& u, float* pk, PairGlob q,
-                                                 int q0, int ga, int gb, bool has_b, float* coef) {
+// NP gate pairs of one lane, side by side in ONE basic block (no branch between the pairs: the parameter phase is a
+// long dependent chain per pair - load, chain rule, MUFU, sin/cos, SU(2) products, rsqrt, rcp - and the instruction
+// scheduler interleaves the independent chains).  Pair k: gates ga[k] and ga[k] + TPS (has_b[k]), q0[k] the position
+// of rotation 0 of its first gate; the fields of a missing gate are zero (heis_kernel zeroes unused positions when it
+// packs the state).  Returns the largest |half angle| seen: arguments beyond the fast range reduction are handled
+// by the caller (heis_kernel), out of line, so that the hot path has no branch.
+template <int TPS, int AX0, int AX1, int AX2, int NP>
+__device__ __forceinline__ float heis_pairs_update(const KParams<float>& p, const UpdCtx<float>& u, float* pk,
+                                                   PairGlob (&q)[NP], const int (&q0)[NP], const int (&ga)[NP],
+                                                   const bool (&has_b)[NP], float* coef) {
   constexpr int SW = HEIS_SU2_WORDS;
-  float* cfa = coef + SW * ga;
-  float* cfb = coef + SW * (has_b ? gb : ga);
   float big = 0.f;
   if (u.phase != PH_COEF) {
-    // gradient sums of the backward sweep, back to the gates' output frames (heis_gate_load)
-    const float4 la = *reinterpret_cast<const float4*>(cfa), lb = *reinterpret_cast<const float4*>(cfb);
-    const float2 px = p2(la.x, lb.x), py = p2(la.y, lb.y), wi = p2(la.z, lb.z), wr = p2(-la.w, -lb.w);
-    float2 sx = fma2(neg2(wi), py, mul2(wr, px)), sy = fma2(wr, py, mul2(wi, px)), sz = p2(cfa[4], cfb[4]);
-    // half-angle cos / sin of the second and third rotation at the parameters of the step being finished: recomputed
-    // (the scalar path keeps them in global memory: 32 bytes of L2 traffic per gate and step)
-    const float2 y1 = mul2(q.th1, bc2(0.5f)), y2 = mul2(q.th2, bc2(0.5f));
-    float2 c2, s2, c3, s3;
-    sincos_core2(y1, s2, c2); sincos_core2(y2, s3, c3);
-    big = fmaxf(fmaxf(fabsf(y1.x), fabsf(y1.y)), fmaxf(fabsf(y2.x), fabsf(y2.y)));
-    if (big > 48000.f) {
-      sincos_inl(y1.x, s2.x, c2.x); sincos_inl(y1.y, s2.y, c2.y); sincos_inl(y2.x, s3.x, c3.x); sincos_inl(y2.y, s3.y, c3.y);
+    float2 g0[NP], g1[NP], g2[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const float* cfa = coef + SW * ga[k];
+      const float* cfb = coef + SW * (has_b[k] ? ga[k] + TPS : ga[k]);
+      // gradient sums of the backward sweep, back to the gates' output frames (heis_gate_load)
+      const float4 la = *reinterpret_cast<const float4*>(cfa), lb = *reinterpret_cast<const float4*>(cfb);
+      const float2 px = p2(la.x, lb.x), py = p2(la.y, lb.y), wi = p2(la.z, lb.z), wr = p2(-la.w, -lb.w);
+      float2 sx = fma2(neg2(wi), py, mul2(wr, px)), sy = fma2(wr, py, mul2(wi, px)), sz = p2(cfa[4], cfb[4]);
+      // half-angle cos / sin of the second and third rotation at the parameters of the step being finished:
+      // recomputed (the scalar path keeps them in global memory: 32 bytes of L2 traffic per gate and step)
+      const float2 y1 = mul2(q[k].th1, bc2(0.5f)), y2 = mul2(q[k].th2, bc2(0.5f));
+      float2 c2, s2, c3, s3;
+      sincos_core2(y1, s2, c2); sincos_core2(y2, s3, c3);
+      // chain rule through G = R_2 R_1 R_0 (heis_su2_update); rotations by -theta: (C, -S) with S = 2 c s
+      const float2 C2 = fma2(c2, c2, neg2(mul2(s2, s2))), t2 = mul2(bc2(2.f), c2), S2 = mul2(t2, s2), nS2 = mul2(neg2(t2), s2);
+      const float2 C3 = fma2(c3, c3, neg2(mul2(s3, s3))), t3 = mul2(bc2(2.f), c3), S3 = mul2(t3, s3), nS3 = mul2(neg2(t3), s3);
+      g2[k] = sel3c<AX2>(sx, sy, sz);
+      rot_axis2<AX2>(C3, nS3, S3, sx, sy, sz);
+      g1[k] = sel3c<AX1>(sx, sy, sz);
+      rot_axis2<AX1>(C2, nS2, S2, sx, sy, sz);
+      g0[k] = sel3c<AX0>(sx, sy, sz);
     }
-    // chain rule through G = R_2 R_1 R_0 (heis_su2_update); rotations by -theta: (C, -S) with S = 2 c s
-    const float2 C2 = fma2(c2, c2, neg2(mul2(s2, s2))), t2 = mul2(bc2(2.f), c2), S2 = mul2(t2, s2), nS2 = mul2(neg2(t2), s2);
-    const float2 C3 = fma2(c3, c3, neg2(mul2(s3, s3))), t3 = mul2(bc2(2.f), c3), S3 = mul2(t3, s3), nS3 = mul2(neg2(t3), s3);
-    const float2 g2 = sel3c<AX2>(sx, sy, sz);
-    rot_axis2<AX2>(C3, nS3, S3, sx, sy, sz);
-    const float2 g1 = sel3c<AX1>(sx, sy, sz);
-    rot_axis2<AX1>(C2, nS2, S2, sx, sy, sz);
-    const float2 g0 = sel3c<AX0>(sx, sy, sz);
-    heis_apply2(p, u, pk, q0 + 4 * TPS, g2, q.th2, q.mu2, q.nu2);
-    heis_apply2(p, u, pk, q0 + 2 * TPS, g1, q.th1, q.mu1, q.nu1);
-    heis_apply2(p, u, pk, q0, g0, q.th0, q.mu0, q.nu0);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      heis_apply2(p, u, pk, q0[k] + 4 * TPS, u.active, g2[k], q[k].th2, q[k].mu2, q[k].nu2);
+      heis_apply2(p, u, pk, q0[k] + 2 * TPS, u.active, g1[k], q[k].th1, q[k].mu1, q[k].nu1);
+      heis_apply2(p, u, pk, q0[k], u.active, g0[k], q[k].th0, q[k].mu0, q[k].nu0);
+    }
   }
   if (!u.skip_coef) {
-    const float2 x0 = mul2(q.th0, bc2(0.5f)), x1 = mul2(q.th1, bc2(0.5f)), x2 = mul2(q.th2, bc2(0.5f));
-    float2 s0, c0, s1, c1, s2, c2;
-    sincos_core2(x0, s0, c0); sincos_core2(x1, s1, c1); sincos_core2(x2, s2, c2);
-    big = fmaxf(fmaxf(fmaxf(fabsf(x0.x), fabsf(x0.y)), fmaxf(fabsf(x1.x), fabsf(x1.y))),
-                fmaxf(fabsf(x2.x), fabsf(x2.y)));
-    if (big > 48000.f) {           // never taken in practice: large-argument reduction out of line
-      sincos_inl(x0.x, s0.x, c0.x); sincos_inl(x0.y, s0.y, c0.y); sincos_inl(x1.x, s1.x, c1.x);
-      sincos_inl(x1.y, s1.y, c1.y); sincos_inl(x2.x, s2.x, c2.x); sincos_inl(x2.y, s2.y, c2.y);
-    }
-    float2 ar, ai, br, bi;
-    su2_two2<AX0, AX1>(c0, s0, c1, s1, ar, ai, br, bi);
-    su2_lmul_axis2<AX2>(c2, s2, ar, ai, br, bi);
-    // ZYZ form for the forward sweep (heis_su2_update)
-    const float2 na = fma2(ar, ar, mul2(ai, ai)), nb = fma2(br, br, mul2(bi, bi));
-    const bool oax = na.x > 1e-30f, oay = na.y > 1e-30f, obx = nb.x > 1e-30f, oby = nb.y > 1e-30f;
-    const float2 zero = bc2(0.f), one = bc2(1.f);
-    const float2 ia = sel2(oax, oay, rsqrt_fast2(na), zero), ib = sel2(obx, oby, rsqrt_fast2(nb), zero);
-    const float2 par = sel2(oax, oay, mul2(ar, ia), one), pai = mul2(ai, ia);
-    const float2 pbr = sel2(obx, oby, mul2(br, ib), one), pbi = mul2(bi, ib);
-    const float2 cyv = mul2(na, ia), syv = mul2(nb, ib);
-    const float2 ty = mul2(neg2(syv), rcp_fast2(add2(one, cyv)));
-    const float2 uor = fma2(pbr, par, mul2(pbi, pai)), uoi = fma2(pbi, par, neg2(mul2(pbr, pai)));
-    const float2 uir = fma2(par, pbr, neg2(mul2(pai, pbi))), uii = neg2(fma2(par, pbi, mul2(pai, pbr)));
-    *reinterpret_cast<float4*>(cfa) = make_float4(ty.x, syv.x, uor.x, uoi.x);
-    *reinterpret_cast<float2*>(cfa + 4) = make_float2(uir.x, uii.x);
-    if (has_b) {
-      *reinterpret_cast<float4*>(cfb) = make_float4(ty.y, syv.y, uor.y, uoi.y);
-      *reinterpret_cast<float2*>(cfb + 4) = make_float2(uir.y, uii.y);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      float* cfa = coef + SW * ga[k];
+      float* cfb = coef + SW * (has_b[k] ? ga[k] + TPS : ga[k]);
+      const float2 x0 = mul2(q[k].th0, bc2(0.5f)), x1 = mul2(q[k].th1, bc2(0.5f)), x2 = mul2(q[k].th2, bc2(0.5f));
+      float2 s0, c0, s1, c1, s2, c2;
+      sincos_core2(x0, s0, c0); sincos_core2(x1, s1, c1); sincos_core2(x2, s2, c2);
+      big = fmaxf(big, fmaxf(fmaxf(fmaxf(fabsf(x0.x), fabsf(x0.y)), fmaxf(fabsf(x1.x), fabsf(x1.y))),
+                             fmaxf(fabsf(x2.x), fabsf(x2.y))));
+      float2 ar, ai, br, bi;
+      su2_two2<AX0, AX1>(c0, s0, c1, s1, ar, ai, br, bi);
+      su2_lmul_axis2<AX2>(c2, s2, ar, ai, br, bi);
+      // ZYZ form for the forward sweep (heis_su2_update)
+      const float2 na = fma2(ar, ar, mul2(ai, ai)), nb = fma2(br, br, mul2(bi, bi));
+      const bool oax = na.x > 1e-30f, oay = na.y > 1e-30f, obx = nb.x > 1e-30f, oby = nb.y > 1e-30f;
+      const float2 zero = bc2(0.f), one = bc2(1.f);
+      const float2 ia = sel2(oax, oay, rsqrt_fast2(na), zero), ib = sel2(obx, oby, rsqrt_fast2(nb), zero);
+      const float2 par = sel2(oax, oay, mul2(ar, ia), one), pai = mul2(ai, ia);
+      const float2 pbr = sel2(obx, oby, mul2(br, ib), one), pbi = mul2(bi, ib);
+      const float2 cyv = mul2(na, ia), syv = mul2(nb, ib);
+      const float2 ty = mul2(neg2(syv), rcp_fast2(add2(one, cyv)));
+      const float2 uor = fma2(pbr, par, mul2(pbi, pai)), uoi = fma2(pbi, par, neg2(mul2(pbr, pai)));
+      const float2 uir = fma2(par, pbr, neg2(mul2(pai, pbi))), uii = neg2(fma2(par, pbi, mul2(pai, pbr)));
+      *reinterpret_cast<float4*>(cfa) = make_float4(ty.x, syv.x, uor.x, uoi.x);
+      *reinterpret_cast<float2*>(cfa + 4) = make_float2(uir.x, uii.x);
+      if (has_b[k]) {
+        *reinterpret_cast<float4*>(cfb) = make_float4(ty.y, syv.y, uor.y, uoi.y);
+        *reinterpret_cast<float2*>(cfb + 4) = make_float2(uir.y, uii.y);
+      }
     }
   }
+  return big;
 }
-// gates g0, g0 + TPS, ... < g_end of one class, two at a time (g0 is the lane's first gate of the class, so the pair
-// (g, g + TPS) shares one 8-byte slot per field); the state of the next pair is requested before the current pair
-// is processed.
+// gates g0, g0 + TPS, ... < g_end of one class: four at a time (two pairs), then the remaining one or two (g0 is the
+// lane's first gate of the class, so the pair (g, g + TPS) shares one 8-byte slot per field).  Returns the largest
+// |half angle| of the new parameters.
 template <int NQ, int TPS, int AX0, int AX1, int AX2>
-__device__ __forceinline__ void heis_su2_loop_pair(const KParams<float>& p, const UpdCtx<float>& u, float* pk, int g0,
-                                                   int g_end, float* coef) {
+__device__ __forceinline__ float heis_su2_loop_pair(const KParams<float>& p, const UpdCtx<float>& u, float* pk, int g0,
+                                                    int g_end, float* coef) {
   int q0 = heis_pk_pos_su2(g0, 0, NQ, TPS);
-  PairGlob qa = heis_pair_load<TPS>(pk, q0, g0 < g_end);
+  float big = 0.f;
+  int g = g0;
 #pragma unroll 1
-  for (int g = g0; g < g_end; g += 4 * TPS) {
+  for (; g + 2 * TPS < g_end; g += 4 * TPS) {
     // consecutive pairs of a lane are 6 TPS positions apart (three rotations x TPS lanes x 2)
-    const PairGlob qb = heis_pair_load<TPS>(pk, q0 + 6 * TPS, g + 2 * TPS < g_end);
-    heis_pair_update<TPS, AX0, AX1, AX2>(p, u, pk, qa, q0, g, g + TPS, g + TPS < g_end, coef);
-    qa = heis_pair_load<TPS>(pk, q0 + 12 * TPS, g + 4 * TPS < g_end);
-    if (g + 2 * TPS < g_end)
-      heis_pair_update<TPS, AX0, AX1, AX2>(p, u, pk, qb, q0 + 6 * TPS, g + 2 * TPS, g + 3 * TPS, g + 3 * TPS < g_end, coef);
+    PairGlob q[2] = {heis_pair_load<TPS>(pk, q0, true), heis_pair_load<TPS>(pk, q0 + 6 * TPS, true)};
+    const int qs[2] = {q0, q0 + 6 * TPS}, gs[2] = {g, g + 2 * TPS};
+    const bool hb[2] = {true, g + 3 * TPS < g_end};
+    big = fmaxf(big, heis_pairs_update<TPS, AX0, AX1, AX2, 2>(p, u, pk, q, qs, gs, hb, coef));
     q0 += 12 * TPS;
   }
+  if (g < g_end) {
+    PairGlob q[1] = {heis_pair_load<TPS>(pk, q0, true)};
+    const int qs[1] = {q0}, gs[1] = {g};
+    const bool hb[1] = {g + TPS < g_end};
+    big = fmaxf(big, heis_pairs_update<TPS, AX0, AX1, AX2, 1>(p, u, pk, q, qs, gs, hb, coef));
+  }
+  return big;
 }
 
 // packed axes of a gate class: a0 | a1 << 4 | a2 << 8 (15 = unused slot); 0xffff = not uniform
@@ -1019,10 +1037,11 @@ __device__ __forceinline__ void heis_su2_loop(const KParams<R>& p, const HSu2* m
 // Entanglers two at a time (float, PLAIN runs, every entangler a CP gate with a parameter): .x is entangler k, .y is
 // k + TPS; same arithmetic per component as the scalar loop in heis_kernel.
 template <int NQ, int TPS>
-__device__ __forceinline__ void heis_cp_loop_pair(const KParams<float>& p, const UpdCtx<float>& u, const HCp* s_cp, float* pk,
-                                                  int cp_base, int m, float* coef, float* coef_cp, float& reg_part) {
+__device__ __forceinline__ float heis_cp_loop_pair(const KParams<float>& p, const UpdCtx<float>& u, const HCp* s_cp, float* pk,
+                                                   int cp_base, int m, float* coef, float* coef_cp, float& reg_part) {
   constexpr int SW = HEIS_SU2_WORDS, CW = HEIS_CP_WORDS;
   const float2 z = make_float2(0.f, 0.f);
+  float big = 0.f;
   int q = cp_base + 2 * m;
   float2 th_n = z, mu_n = z, nu_n = z;
   if (m < p.n_cp) {
@@ -1049,13 +1068,13 @@ __device__ __forceinline__ void heis_cp_loop_pair(const KParams<float>& p, const
     float* rsb = coef + SW * (NQ + 2 * (has_b ? kb : k) + 1) + 6;
     if (u.phase != PH_COEF) {
       const float2 g = add2(p2(cfa[0], cfb[0]), p2(*rsa, *rsb));
-      heis_apply2(p, u, pk, q, g, th, mu, nu);
+      heis_apply2(p, u, pk, q, u.active, g, th, mu, nu);
     }
     if (!u.skip_coef) {
       const float2 x = mul2(th, bc2(0.5f));
       float2 s, c;
       sincos_core2(x, s, c);
-      if (fmaxf(fabsf(x.x), fabsf(x.y)) > 48000.f) { sincos_inl(x.x, s.x, c.x); sincos_inl(x.y, s.y, c.y); }
+      big = fmaxf(big, fmaxf(fabsf(x.x), fabsf(x.y)));       // beyond the fast reduction: redone by the caller
       float rs_a = 0.f, rs_b = 0.f;
       if (pen_a) {
         float val, slope;
@@ -1079,16 +1098,19 @@ __device__ __forceinline__ void heis_cp_loop_pair(const KParams<float>& p, const
     }
     q += 2 * TPS;
   }
+  return big;
 }
 
+// pairs: the packed two-gates-per-thread path may be used (float Adam runs without freeze mask / history whose fused
+// gates are all-parameter); returns the largest |half angle| it met (0 from the scalar loops, which reduce large
+// arguments themselves)
 template <typename R, int NQ, int TPS>
-__device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KParams<R>& p, const HSu2* ms,
-                                                  const UpdCtx<R>& u, R* pk, int g0, int g_end, R* coef, R* aux) {
+__device__ __forceinline__ R heis_su2_loop_any(int axp, bool plain, bool pairs, const KParams<R>& p, const HSu2* ms,
+                                               const UpdCtx<R>& u, R* pk, int g0, int g_end, R* coef, R* aux) {
   if constexpr (sizeof(R) == 4) {
-    // float Adam runs without freeze mask / history whose fused gates are all-parameter: two gates per thread, packed
-    if (plain && p.su2_all_params) {
-      if (axp == AXP_XYZ) { heis_su2_loop_pair<NQ, TPS, 0, 1, 2>(p, u, pk, g0, g_end, coef); return; }
-      if (axp == AXP_ZXZ) { heis_su2_loop_pair<NQ, TPS, 2, 0, 2>(p, u, pk, g0, g_end, coef); return; }
+    if (pairs) {
+      if (axp == AXP_XYZ) return heis_su2_loop_pair<NQ, TPS, 0, 1, 2>(p, u, pk, g0, g_end, coef);
+      if (axp == AXP_ZXZ) return heis_su2_loop_pair<NQ, TPS, 2, 0, 2>(p, u, pk, g0, g_end, coef);
     }
   }
   if (axp == AXP_XYZ) {
@@ -1099,6 +1121,7 @@ __device__ __forceinline__ void heis_su2_loop_any(int axp, bool plain, const KPa
     else heis_su2_loop<R, NQ, TPS, 2, 0, 2, false>(p, ms, u, pk, g0, g_end, coef, aux);
   } else if (axp == AXP_XZ) heis_su2_loop<R, NQ, TPS, 0, 2, -1, false>(p, ms, u, pk, g0, g_end, coef, aux);
   else heis_su2_loop<R, NQ, TPS, -2, -2, -2, false>(p, ms, u, pk, g0, g_end, coef, aux);
+  return R(0);
 }
 
 // f(parameter index or -1, position) for every position of the packed state that lane m of a sample owns: the slots of
@@ -1248,18 +1271,15 @@ heis_kernel(const KParams<R> p) {
       // split and time-sliced runs are bit-identical to one launch by construction, not by the compiler's choice of
       // identical FMA contractions in two instantiations
       const bool plain = p.mode == M_ADAM && p.freeze == nullptr && p.hist_params == nullptr;
-      heis_su2_loop_any<R, NQ, TPS>(p.axp_surface, plain, p, s_su2, u, pk, m, NQ < p.n_su2 ? NQ : p.n_su2, coef, aux);
-      heis_su2_loop_any<R, NQ, TPS>(p.axp_block, plain, p, s_su2, u, pk, NQ + m, p.n_su2, coef, aux);
+      const int n_surf = NQ < p.n_su2 ? NQ : p.n_su2;
+      const bool pairs = sizeof(R) == 4 && plain && p.su2_all_params;
+      R big = heis_su2_loop_any<R, NQ, TPS>(p.axp_surface, plain, pairs, p, s_su2, u, pk, m, n_surf, coef, aux);
+      big = fmax(big, heis_su2_loop_any<R, NQ, TPS>(p.axp_block, plain, pairs, p, s_su2, u, pk, NQ + m, p.n_su2, coef, aux));
       // entangler angles, software pipelined like the fused-gate loops: the packed state of the next gate is
       // requested before the current one is processed
-      bool cp_done = false;
-      if constexpr (sizeof(R) == 4) {
-        if (plain && p.cp_all_params) {
-          heis_cp_loop_pair<NQ, TPS>(p, u, s_cp, pk, cp_base, m, coef, coef_cp, reg_part);
-          cp_done = true;
-        }
-      }
-      if (!cp_done) {
+      const bool cp_pairs = sizeof(R) == 4 && plain && p.cp_all_params;
+      auto cp_scalar = [&](const UpdCtx<R>& u) {
+        const int phase = u.phase;
         int k = m;
         int pi_n = -1;
         Pk4<R> v_n = Pk4<R>{R(0), R(0), R(0), R(0)};
@@ -1298,6 +1318,24 @@ heis_kernel(const KParams<R> p) {
             if (c < R(0)) { c = -c; s = -s; }
             cf[0] = c; cf[1] = s; cf[2] = -s * rcp_fast(R(1) + c); *rsw = rs;
           }
+        }
+      };
+      if constexpr (sizeof(R) == 4) {
+        if (cp_pairs) big = fmax(big, heis_cp_loop_pair<NQ, TPS>(p, u, s_cp, pk, cp_base, m, coef, coef_cp, reg_part));
+      }
+      if (!cp_pairs) cp_scalar(u);
+      if constexpr (sizeof(R) == 4) {
+        // The packed paths reduce sin / cos arguments with the three-constant scheme only; a half angle beyond its
+        // range (never seen in an optimisation: |theta| > 96000) sends the whole warp once more through the scalar
+        // loops, coefficients only, whose sin / cos fall back to the library reduction.
+        if ((pairs || cp_pairs) && !u.skip_coef && __any_sync(0xffffffffu, big > R(48000))) {
+          UpdCtx<R> u2 = u;
+          u2.phase = PH_COEF;
+          if (pairs) {
+            heis_su2_loop_any<R, NQ, TPS>(p.axp_surface, false, false, p, s_su2, u2, pk, m, n_surf, coef, aux);
+            heis_su2_loop_any<R, NQ, TPS>(p.axp_block, false, false, p, s_su2, u2, pk, NQ + m, p.n_su2, coef, aux);
+          }
+          if (cp_pairs) { reg_part = R(0); cp_scalar(u2); }
         }
       }
     }
