@@ -162,12 +162,15 @@ struct HeisSweep {
     ry_fwd<PA>(yr, yi, cl);
     ry_fwd<PC>(yr, yi, ch);
   }
-  template <int J>
+  // CHECKED: the (one) partial layer at the end of the template; full layers run without the per-block tests (an
+  // early exit after every block costs a compare, a branch and ~8 register moves that bring the state back to the
+  // loop's register assignment)
+  template <int J, bool CHECKED>
   static __device__ __forceinline__ void blocks_fwd(int k0, int K, const R* cs, V (&yr)[N], V (&yi)[N]) {
     if constexpr (J < NBL) {
-      if (k0 + J >= K) return;
+      if (CHECKED && k0 + J >= K) return;
       block_fwd<NQ - 1 - lo_q(J), NQ - 1 - hi_q(J)>(cs + 2 * SW * J, yr, yi);
-      blocks_fwd<J + 1>(k0, K, cs, yr, yi);
+      blocks_fwd<J + 1, CHECKED>(k0, K, cs, yr, yi);
     }
   }
   static __device__ __forceinline__ void forward(const KParams<R>& p, const LayerBar lb, const HCp*, const R* coef,
@@ -176,11 +179,13 @@ struct HeisSweep {
     const int K = p.n_cp;
     const R* cs = coef + SW * NQ;
     if (lb.fwd) __syncthreads();
+    int k0 = 0;
 #pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += NBL) {
-      blocks_fwd<0>(k0, K, cs, yr, yi);
+    for (; k0 + NBL <= K; k0 += NBL) {
+      blocks_fwd<0, false>(k0, K, cs, yr, yi);
       cs += 2 * SW * NBL;
     }
+    if (k0 < K) blocks_fwd<0, true>(k0, K, cs, yr, yi);
     tail_fwd<0>(p, yr, yi, coef);
   }
 
@@ -369,12 +374,12 @@ struct HeisSweep {
     su2_bwd<PA>(h, st, cl, m);
     phase_bwd<PA, PC>(h, cph, m);
   }
-  template <int J>
+  template <int J, bool CHECKED>
   static __device__ __forceinline__ void blocks_bwd(int k0, int K, R* cs, const R* stage, R* cph, int m, V (&h)[N]) {
     if constexpr (J >= 0) {
-      if (k0 + J < K)
+      if (!CHECKED || k0 + J < K)
         block_bwd<NQ - 1 - lo_q(J), NQ - 1 - hi_q(J)>(h, stage + STW * (2 * J), cs + 2 * SW * J, cph + CW * J, m);
-      blocks_bwd<J - 1>(k0, K, cs, stage, cph, m, h);
+      blocks_bwd<J - 1, CHECKED>(k0, K, cs, stage, cph, m, h);
     }
   }
   template <int Q>
@@ -428,11 +433,18 @@ struct HeisSweep {
     const int K = p.n_cp;
     if (lb.bwd) __syncthreads();
     tail_bwd<0>(p, coef, m, h);
-#pragma unroll 1
-    for (int k0 = K > 0 ? ((K - 1) / NBL) * NBL : -1; k0 >= 0; k0 -= NBL) {
+    int k0 = (K / NBL) * NBL;          // first block of the partial layer, if there is one
+    if (k0 < K) {
       stage_layer(k0, K, coef, cph0, stage, m);
       __syncwarp();
-      blocks_bwd<NBL - 1>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
+      blocks_bwd<NBL - 1, true>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (k0 -= NBL; k0 >= 0; k0 -= NBL) {
+      stage_layer(k0, K, coef, cph0, stage, m);
+      __syncwarp();
+      blocks_bwd<NBL - 1, false>(k0, K, coef + SW * NQ + 2 * SW * k0, stage, cph0 + CW * k0, m, h);
       __syncwarp();
     }
     stage_surface(coef, stage, m);
