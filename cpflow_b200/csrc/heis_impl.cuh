@@ -98,6 +98,17 @@ __device__ __forceinline__ void sts_if(bool on, double* q, double v) {
                "r"((unsigned)__cvta_generic_to_shared(q)), "d"(v) : "memory");
 }
 
+// two adjacent words in one predicated store (q 8 / 16 bytes aligned): two predicated scalar stores under the same
+// predicate come out of ptxas as a BSSY / BRA / BSYNC region
+__device__ __forceinline__ void sts2_if(bool on, float* q, float v0, float v1) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.shared.v2.f32 [%1], {%2, %3}; }" ::"r"((int)on),
+               "r"((unsigned)__cvta_generic_to_shared(q)), "f"(v0), "f"(v1) : "memory");
+}
+__device__ __forceinline__ void sts2_if(bool on, double* q, double v0, double v1) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.shared.v2.f64 [%1], {%2, %3}; }" ::"r"((int)on),
+               "r"((unsigned)__cvta_generic_to_shared(q)), "d"(v0), "d"(v1) : "memory");
+}
+
 template <typename V> struct AddV;
 template <> struct AddV<float> { static __device__ __forceinline__ float add(float a, float b) { return a + b; }
                                  static __device__ __forceinline__ float sub(float a, float b) { return a - b; } };
@@ -242,7 +253,7 @@ struct HeisSweep {
     constexpr int BM = 1 << B;
     if constexpr (B < PB) {
       const bool own = m == 0;
-      sts_if(own, sl, T::get(hv[0], 1)); sts_if(own, sl + 1, T::get(hv[BM], 1)); sts_if(own, sl + 4, T::get(hv[BM], 0));
+      sts2_if(own, sl, T::get(hv[0], 1), T::get(hv[BM], 1)); sts_if(own, sl + 4, T::get(hv[BM], 0));
       // x bit = xr: I = h[0][z], Z = h[0][z|1], X = h[1][z], Y = h[1][z|1]
       R ct, st, cz, sz;
       Vec4Load<R>::ld(cf + 4, ct, st, cz, sz);
@@ -264,7 +275,7 @@ struct HeisSweep {
       constexpr int J = B - PB;
       const bool mb = ((m >> J) & 1) != 0;
       const bool own = m == (1 << J);
-      sts_if(own, sl, T::get(hv[0], 0)); sts_if(own, sl + 1, T::get(hv[BM], 0));
+      sts2_if(own, sl, T::get(hv[0], 0), T::get(hv[BM], 0));
       sts_if(m == 0, sl + 4, T::get(hv[BM], 0));
       R ct, st, cz, sz;
       Vec4Load<R>::ld(cf + (mb ? 4 : 0), ct, st, cz, sz);
