@@ -257,18 +257,15 @@ struct HeisSweep {
       // x bit = xr: I = h[0][z], Z = h[0][z|1], X = h[1][z], Y = h[1][z|1]
       R ct, st, cz, sz;
       Vec4Load<R>::ld(cf + 4, ct, st, cz, sz);
-      // Rx mixes the two halves of hv[z | BM] = (Z, Y): one packed multiply-add with the swapped register
-      // ((Z', Y') = ct (Z, Y) + (-st, st) (Y, Z)); every FP instruction, packed or scalar, costs the same issue time
-      // next to packed ones (tools/issue_mix.cu), so 2 packed + 4 scalar beat 8 scalar
-      const V kct = T::bc(ct), kms = T::make(-st, st);
+      // (scalar on purpose: Rx mixes the two halves of hv[z | BM] = (Z, Y); the packed form ct (Z, Y) + (-st, st) (Y, Z)
+      // was measured: the same FMA-pipe time, plus two register moves per pair for the swapped operand)
 #pragma unroll
       for (int z = 0; z < N; ++z) {
         if (z & BM) continue;
-        const V h1 = hv[z | BM];
-        const V n1 = T::fma(kms, T::make(T::get(h1, 1), T::get(h1, 0)), T::mul(kct, h1));
-        const R X = T::get(hv[z], 1), Y1 = T::get(n1, 1);
+        const R X = T::get(hv[z], 1), Y = T::get(hv[z | BM], 1), Z = T::get(hv[z | BM], 0);
+        const R Y1 = ct * Y + st * Z;
         hv[z] = T::make(T::get(hv[z], 0), cz * X + sz * Y1);
-        hv[z | BM] = T::make(T::get(n1, 0), cz * Y1 - sz * X);
+        hv[z | BM] = T::make(ct * Z - st * Y, cz * Y1 - sz * X);
       }
     } else {
       // x bit is lane bit J: lanes with the bit clear hold (I, Z), lanes with it set hold (X, Y)
@@ -1011,7 +1008,8 @@ __device__ __forceinline__ float heis_su2_loop_pair(const KParams<float>& p, con
   int g = g0;
 #pragma unroll 1
   for (; g + 2 * TPS < g_end; g += 4 * TPS) {
-    // consecutive pairs of a lane are 6 TPS positions apart (three rotations x TPS lanes x 2)
+    // consecutive pairs of a lane are 6 TPS positions apart (three rotations x TPS lanes x 2).  (Requesting the angles
+    // of the next four gates one iteration ahead was measured: no gain, 143.7 vs 143.2 ms on the C3 shape.)
     PairGlob q[2] = {heis_pair_load<TPS>(pk, q0, true), heis_pair_load<TPS>(pk, q0 + 6 * TPS, true)};
     const int qs[2] = {q0, q0 + 6 * TPS}, gs[2] = {g, g + 2 * TPS};
     const bool hb[2] = {true, g + 3 * TPS < g_end};
