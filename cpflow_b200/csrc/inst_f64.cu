@@ -9,10 +9,11 @@ int launch_engine<double>(const KParams<double>& p, int n, bool single, cudaStre
     switch (n) {
       case 2: return launch_one<double, 2, 2, 1, true>(p, st, err);
       case 3: return launch_one<double, 3, 2, 1, true>(p, st, err);
-      case 4: return launch_one<double, 4, 2, 1, true>(p, st, err);
-      case 5: return launch_one<double, 5, 3, 1, true>(p, st, err);
-      case 6: return launch_one<double, 6, 3, 1, true>(p, st, err);
-      case 7: return launch_one<double, 7, 4, 1, true>(p, st, err);
+      // (register bits as in inst_f32.cu: more lanes per sample = more resident warps)
+      case 4: return launch_one<double, 4, 1, 1, true>(p, st, err);
+      case 5: return launch_one<double, 5, 1, 1, true>(p, st, err);
+      case 6: return launch_one<double, 6, 2, 1, true>(p, st, err);
+      case 7: return launch_one<double, 7, 2, 1, true>(p, st, err);
     }
   } else {
     switch (n) {
@@ -30,7 +31,7 @@ int launch_engine<double>(const KParams<double>& p, int n, bool single, cudaStre
 template <>
 int engine_rb<double>(int n, bool single) {
   if (single) {
-    switch (n) { case 2: return 2; case 3: return 2; case 4: return 2; case 5: return 3; case 6: return 3; case 7: return 4; }
+    switch (n) { case 2: return 2; case 3: return 2; case 4: return 1; case 5: return 1; case 6: return 2; case 7: return 2; }
   } else {
     switch (n) { case 2: return 2; case 3: return 2; case 4: return 3; case 5: return 5; }
   }
