@@ -8,9 +8,26 @@ namespace cpf {
 template <>
 bool launch_layered<float>(const KParams<float>& p, const Program& prog, bool single, cudaStream_t st,
                            std::string& err, int& rc) {
-  if (single) return false;   // state preparation: interpreter kernel
   const int n = prog.n_qubits, nb = prog.period;
   const unsigned long long lo = prog.lo_pack, hi = prog.hi_pack;
+  if (single) {
+    // state preparation (one column per sample) on the standard 4- and 5-qubit layers (+17 % / +20 % over the
+    // interpreter kernel); register bits as in inst_f32.cu (single_rb_f32).  Other layers: interpreter kernel.
+#define CPF_SINGLE_LAYER(N_, RB_, NB_, LO_, HI_)                                                                  \
+    if (n == N_ && nb == NB_ && lo == LO_ && hi == HI_) {                                                          \
+      rc = launch_one<float, N_, RB_, 1, true, LayerSweep<float, N_, RB_, 1, true, NB_, LO_, HI_>>(p, st, err);    \
+      return true;                                                                                                 \
+    }
+    CPF_SINGLE_LAYER(4, 1, 3, 0x210ull, 0x321ull)                    // 4q chain
+    CPF_SINGLE_LAYER(4, 1, 3, 0x0ull, 0x321ull)                      // 4q star
+    CPF_SINGLE_LAYER(4, 1, 6, 0x211000ull, 0x332321ull)              // 4q connected
+    CPF_SINGLE_LAYER(5, 1, 4, 0x3210ull, 0x4321ull)                  // 5q chain
+    CPF_SINGLE_LAYER(5, 1, 10, 0x3221110000ull, 0x4434324321ull)     // 5q connected
+    // (6 and 7 qubits: the straight-line sweeps were measured slower than the interpreter, 31.2 vs 34.7 and 18.3 vs
+    // 20.5 M evals/s on the chain templates with K = 60 - profiles/r2_exp_single_rb.txt)
+#undef CPF_SINGLE_LAYER
+    return false;
+  }
   // 2q chain [(0, 1)]
   if (n == 2 && nb == 1 && lo == 0x0ull && hi == 0x1ull) {
     rc = launch_one<float, 2, 2, 2, false, LayerSweep<float, 2, 2, 2, false, 1, 0x0ull, 0x1ull>>(p, st, err);
