@@ -521,7 +521,7 @@ engine_kernel(const KParams<R> p) {
           R g = R(-2) * cf[0];
           if (pen_on) {
             R val, slope;
-            penalty_eval(p.pen, th, val, slope);
+            penalty_eval_fast(p.pen, th, val, slope);
             g = add_rn(g, mul_rn(p.pen.r, slope));
           }
           apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi, g, th);
@@ -532,7 +532,7 @@ engine_kernel(const KParams<R> p) {
           cf[0] = c; cf[1] = s;
           if (pen_on) {
             R val, slope;
-            penalty_eval(p.pen, th, val, slope);
+            penalty_eval_fast(p.pen, th, val, slope);
             reg_part += val;
           }
         }
