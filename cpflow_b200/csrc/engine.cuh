@@ -546,7 +546,10 @@ struct Cfg {
   static constexpr int NA = 1 << RB;
   static constexpr int COLS = SINGLE ? 1 : N;
   static constexpr int TPS = (COLS / CPT) << LB;     // threads per sample (<= 32)
-  static constexpr int BLOCK = 128;
+#ifndef CPF_SINGLE_BLOCK
+#define CPF_SINGLE_BLOCK 128
+#endif
+  static constexpr int BLOCK = SINGLE ? CPF_SINGLE_BLOCK : 128;
   static constexpr int SPB = BLOCK / TPS;            // samples per block
   static_assert(RB >= 0 && RB <= NQ, "bad register/lane split");
   static_assert(TPS >= 1 && TPS <= 32, "a sample must fit in one warp");

@@ -88,10 +88,11 @@ __device__ __forceinline__ void apply_grad(const KParams<R>& p, bool active, lon
 
 // resident CTAs per SM the register allocator is asked to allow for (state registers per thread
 // = 4 * 2^RB * CPT * sizeof(R)/4 for phi and lambda together)
-template <typename R, int RB, int CPT>
+template <typename R, int RB, int CPT, int BLOCK = 128>
 __host__ __device__ constexpr int min_blocks() {
   constexpr int state = 4 * (1 << RB) * CPT * (int)(sizeof(R) / 4);
-  return state <= 32 ? 5 : (state <= 64 ? 4 : (state <= 128 ? 2 : 1));
+  constexpr int mb = state <= 32 ? 5 : (state <= 64 ? 4 : (state <= 128 ? 2 : 1));
+  return mb * BLOCK > 640 ? (640 / BLOCK > 0 ? 640 / BLOCK : 1) : mb;      // the same threads per SM for every block size
 }
 
 // ---- compile-time dispatch of the decoded ops -------------------------------------------------
@@ -392,7 +393,7 @@ struct LayerSweep {
 };
 
 template <typename R, int NQ, int RB, int CPT, bool SINGLE, typename SW>
-__global__ void __launch_bounds__(Cfg<R, NQ, RB, CPT, SINGLE>::BLOCK, min_blocks<R, RB, CPT>())
+__global__ void __launch_bounds__(Cfg<R, NQ, RB, CPT, SINGLE>::BLOCK, min_blocks<R, RB, CPT, Cfg<R, NQ, RB, CPT, SINGLE>::BLOCK>())
 engine_kernel(const KParams<R> p) {
   using C = Cfg<R, NQ, RB, CPT, SINGLE>;
   using CO = Cols<R, RB, CPT>;
@@ -544,6 +545,9 @@ engine_kernel(const KParams<R> p) {
     // ---------------- forward sweep: U e_col ----------------
 #pragma unroll
     for (int r = 0; r < NA; ++r) { pr[r] = T::onehot((la << RB) | r, col0); pi[r] = T::bc(R(0)); }
+    // (CTA barrier at the sweep starts: the warps of a CTA walk the straight-line sweeps together and share the
+    // instruction cache, see heis_impl.cuh; set per launch by launch_one)
+    if (p.sync_sweeps & 1) __syncthreads();
     SW::forward(p, coef, s_dec, la, pr, pi);
 
     if (p.mode == M_UNITARY) {
@@ -633,6 +637,7 @@ engine_kernel(const KParams<R> p) {
     }
 
     // ---------------- adjoint sweep ----------------
+    if (p.sync_sweeps & 2) __syncthreads();
     SW::backward(p, coef, s_dec, s_red, la, ls, pr, pi, lr, li);
     __syncwarp();
   }

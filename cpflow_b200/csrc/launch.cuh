@@ -24,6 +24,11 @@ int launch_one(KParams<R> p, cudaStream_t st, std::string& err) {
   using C = Cfg<R, NQ, RB, CPT, SINGLE>;
   if (!SW::USES_SCHED) { p.n_sched = 0; p.n_red = 0; }
   p.coef_stride = coef_stride_words(p.n_su2, p.n_cp);
+  // CTA barrier at the sweep starts for the straight-line layered sweeps (the warps of a CTA then share the
+  // instruction cache: state preparation n = 5 54.5 -> 66.1 M evals/s, relative-phase loss 24 -> 29.6 M); the
+  // interpreter's sweep is a small loop and runs without.  CPF_ENGINE_SYNC overrides (measurements).
+  p.sync_sweeps = SW::USES_SCHED ? 0 : 3;
+  if (const char* e = getenv("CPF_ENGINE_SYNC")) { int v = atoi(e); if (v >= 0 && v <= 3) p.sync_sweeps = v; }
   const size_t smem = (size_t)p.target_bytes + (size_t)((p.n_sched + 1) & ~1) * 8 + (size_t)p.n_red * 16 +
                       (size_t)C::SPB * p.coef_stride * sizeof(R);
   if (smem > 227 * 1024) {
