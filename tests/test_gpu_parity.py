@@ -647,3 +647,72 @@ def test_caller_owned_workspace():
     st.workspace = torch.empty(need + 64, dtype=torch.uint8, device=DEV)[8:]
     with pytest.raises(L.CpflowError, match="aligned"):
         anz.program.adam_run(st, Loss("state", V[:, 0].copy()), pen(), 0.1, 2)
+
+
+def test_packed_update_matches_the_scalar_update():
+    """The packed two-gates-per-thread parameter phase (float runs without freeze mask / history) against the scalar
+    loops (the same run with a parameter history, which takes them): the first step is identical up to the rounding
+    of the gradient, the loop stays within the usual f32 trajectory tolerances; lane-interleaved state: every
+    parameter comes back to its own place (angles, moments, best parameters)."""
+    for n, layer, K in ((4, chain_layer(4), 40), (3, chain_layer(3), 7), (4, [[0, 1], [0, 2], [0, 3]], 11)):
+        anz = Ansatz(n, "cp", fill_layers(layer, K))
+        V = unitary_group.rvs(2 ** n, random_state=n + K)
+        a = anz.program.initial_angles(11, 96)
+        for T in (1, 12):
+            fast = anz.program.adam_state(a.clone())
+            anz.program.adam_run(fast, Loss("hs", V), pen(), 0.1, T)
+            slow = anz.program.adam_state(a.clone(), hist_len=T)
+            anz.program.adam_run(slow, Loss("hs", V), pen(), 0.1, T)
+            assert torch.equal(fast.init_regloss, slow.init_regloss) or \
+                float((fast.init_regloss - slow.init_regloss).abs().max()) < 2e-6
+            tol_a = 2e-5 if T == 1 else 2e-2
+            # (T = 1: components with a tiny gradient move by lr g / (|g| + eps); compare moments instead of angles)
+            assert float((fast.m - slow.m).abs().max()) < 2e-6 * max(1.0, float(slow.m.abs().max())) or T > 1
+            assert float((fast.best_regloss - slow.best_regloss).abs().max()) < 2e-4
+            if T > 1:
+                assert float((fast.angles - slow.angles).abs().max()) < tol_a
+            assert torch.equal(fast.best_params, a) if T == 1 else True
+
+
+def test_large_angles_leave_the_fast_range_reduction():
+    """Half angles beyond the three-constant sin / cos reduction of the packed parameter phase (|theta| > 96 000): the
+    warp redoes its coefficients through the scalar loops (heis_kernel: deferred large-argument fix-up), so the
+    losses of such a batch equal those of the scalar path (loss_grad mode and a history run)."""
+    anz = Ansatz(4, "cp", fill_layers(chain_layer(4), 10))
+    V = unitary_group.rvs(16, random_state=3)
+    rng = np.random.default_rng(0)
+    a = torch.tensor(rng.uniform(-3e5, 3e5, (40, anz.num_angles)), dtype=torch.float32, device=DEV)
+    a[::2] = torch.tensor(rng.uniform(0, 6.28, (20, anz.num_angles)), dtype=torch.float32, device=DEV)   # mixed warp
+    lo, rg_, _ = anz.program.loss_grad(a, Loss("hs", V), pen(), want_grad=False)
+    fast = anz.program.adam_state(a.clone())
+    anz.program.adam_run(fast, Loss("hs", V), pen(), 0.1, 1)
+    slow = anz.program.adam_state(a.clone(), hist_len=1)
+    anz.program.adam_run(slow, Loss("hs", V), pen(), 0.1, 1)
+    assert float((fast.init_regloss - (lo + rg_)).abs().max()) < 2e-6
+    assert float((fast.init_regloss - slow.init_regloss).abs().max()) < 2e-6
+    # the oracle on the same float32 angles (range reduction in double)
+    oanz = O.cp_ansatz(chain_layer(4), 10)
+    ol = O.loss_and_grad_batched(4, O.ansatz_program(oanz), a.cpu().double(), "hs", torch.tensor(V), oanz.cp_mask, 0.0,
+                                 O.make_regularization_function())[0]
+    assert float((lo.cpu().double() - ol).abs().max()) < 1e-5
+
+
+def test_parameters_that_feed_no_gate():
+    """A program whose parameter vector is longer than its gates use (the packed optimiser state holds referenced
+    parameters only): the unused entries keep their angles, get zero moments and their own value as best parameter."""
+    from cpflow_b200.engine import Program
+    anz = Ansatz(3, "cp", fill_layers(chain_layer(3), 6))
+    ops, P = anz.program.ops, anz.num_angles
+    prog = Program(3, ops, P + 3)
+    ref = Program(3, ops, P)
+    V = unitary_group.rvs(8, random_state=1)
+    a = torch.tensor(np.random.default_rng(2).uniform(0, 6.28, (33, P + 3)), dtype=torch.float32, device=DEV)
+    for hist in (False, True):
+        st = prog.adam_state(a.clone(), hist_len=7 if hist else 0)
+        prog.adam_run(st, Loss("hs", V), None, 0.1, 7)
+        rf = ref.adam_state(a[:, :P].contiguous().clone(), hist_len=7 if hist else 0)
+        ref.adam_run(rf, Loss("hs", V), None, 0.1, 7)
+        assert torch.equal(st.angles[:, :P], rf.angles) and torch.equal(st.best_regloss, rf.best_regloss)
+        assert torch.equal(st.best_params[:, :P], rf.best_params) and torch.equal(st.m[:, :P], rf.m)
+        assert torch.equal(st.angles[:, P:], a[:, P:]) and torch.equal(st.best_params[:, P:], a[:, P:])
+        assert float(st.m[:, P:].abs().max()) == 0.0 and float(st.v[:, P:].abs().max()) == 0.0
