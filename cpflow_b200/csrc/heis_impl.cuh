@@ -369,10 +369,6 @@ struct HeisSweep {
       }
     }
   }
-  static __device__ __forceinline__ void setc(V& v, int k, R x) {
-    if constexpr (CPT == 2) { if (k) v.y = x; else v.x = x; }
-    else v = x;
-  }
 
   // one block of the backward sweep; st: staged rows of the block's two gates (lower, higher), cl: slot of the
   // lower-qubit gate, cph: the entangler's words

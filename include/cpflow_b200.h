@@ -189,7 +189,8 @@ int cpf_adam_run(const cpf_program* prog, const cpf_loss_spec* loss,
                  void* stream);
 
 /* Device scratch one cpf_adam_run (or cpf_loss_grad) call on `batch` samples needs: the packed optimiser state
- * (16 bytes per parameter and sample on the Heisenberg-picture kernel), the staged target and the penalty mask.
+ * (16 bytes per parameter position and sample on the Heisenberg-picture kernel; positions are the parameters padded
+ * to the lanes' pair slots, see heis_impl.cuh: heis_pk_stride), the staged target and the penalty mask.
  * Callers that manage device memory themselves allocate this once and pass it in cpf_adam_buffers.workspace. */
 int cpf_workspace_bytes(const cpf_program* prog, int32_t loss_kind, int32_t dtype, int64_t batch, int64_t* bytes);
 
