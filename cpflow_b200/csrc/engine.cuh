@@ -271,6 +271,32 @@ static __device__ __noinline__ AdamOut<R> adam_step(R g, R th, R mu, R nu, R b1,
   return {th, mu, nu};
 }
 
+// The same step inside the fused loops of the kernels.  double: the exact IEEE sequence above.  float: reciprocal bias
+// corrections (ibc = 1 / bc, computed once per step), approximate sqrt and reciprocal (<= 2 ulp each) instead of three
+// IEEE divisions and a square root per parameter (in the state-adjoint kernels these were 9 % of the time of a
+// state-preparation run); the arithmetic of heis_impl.cuh: adam_inl.
+__device__ __forceinline__ AdamOut<double> adam_step_fused(double g, double th, double mu, double nu, double b1, double omb1,
+                                                           double b2, double omb2, double bc1, double bc2, double, double,
+                                                           double eps, double neg_lr) {
+  mu = add_rn(mul_rn(omb1, g), mul_rn(b1, mu));
+  nu = add_rn(mul_rn(omb2, mul_rn(g, g)), mul_rn(b2, nu));
+  const double mu_hat = mu / bc1, nu_hat = nu / bc2;
+  th = add_rn(th, mul_rn(neg_lr, mu_hat / add_rn(sqrt(nu_hat), eps)));
+  return {th, mu, nu};
+}
+__device__ __forceinline__ AdamOut<float> adam_step_fused(float g, float th, float mu, float nu, float b1, float omb1,
+                                                          float b2, float omb2, float, float, float ibc1, float ibc2,
+                                                          float eps, float neg_lr) {
+  mu = add_rn(mul_rn(omb1, g), mul_rn(b1, mu));
+  nu = add_rn(mul_rn(omb2, mul_rn(g, g)), mul_rn(b2, nu));
+  const float mu_hat = mu * ibc1, nu_hat = nu * ibc2;
+  float rt, iv;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(nu_hat));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iv) : "f"(add_rn(rt, eps)));
+  th = add_rn(th, mul_rn(neg_lr, mul_rn(mu_hat, iv)));
+  return {th, mu, nu};
+}
+
 // rotate vector (x,y,z) by angle with cos C, sin S about coordinate axis `a` (right-handed):
 // R_a(theta) sigma_b R_a(theta)^dagger = sum_c [Rot_a(theta)]_{cb} sigma_c
 template <typename R>

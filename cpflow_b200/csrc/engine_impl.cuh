@@ -67,7 +67,7 @@ enum Phase : int { PH_COEF = 0, PH_ADAM = 1, PH_GRAD = 2 };
 // one optax-Adam step on the parameter (skipped for frozen parameters: cp_utils.py:100-108).
 template <typename R>
 __device__ __forceinline__ void apply_grad(const KParams<R>& p, bool active, long long b, int phase,
-                                           long long gi, R bc1, R bc2, R* ang, R* mom, R* vel,
+                                           long long gi, R bc1, R bc2, R ibc1, R ibc2, R* ang, R* mom, R* vel,
                                            const uint8_t* frz, int pi, R g, R& th) {
   const int P = p.P;
   if (phase == PH_GRAD) {
@@ -78,7 +78,7 @@ __device__ __forceinline__ void apply_grad(const KParams<R>& p, bool active, lon
   if (!(frz && frz[pi])) {
     const R mu0 = gi == 0 ? R(0) : mom[pi];
     const R nu0 = gi == 0 ? R(0) : vel[pi];
-    const AdamOut<R> o = adam_step(g, th, mu0, nu0, p.b1, p.omb1, p.b2, p.omb2, bc1, bc2, p.eps, -p.lr);
+    const AdamOut<R> o = adam_step_fused(g, th, mu0, nu0, p.b1, p.omb1, p.b2, p.omb2, bc1, bc2, ibc1, ibc2, p.eps, -p.lr);
     th = o.th;
     if (active) { mom[pi] = o.mu; vel[pi] = o.nu; ang[pi] = th; }
   }
@@ -464,10 +464,11 @@ engine_kernel(const KParams<R> p) {
     {
       const long long gu = gi - 1;            // the step being finished
       const bool skip_coef = it == p.nsteps;
-      R bc1 = R(1), bc2 = R(1);
+      R bc1 = R(1), bc2 = R(1), ibc1 = R(1), ibc2 = R(1);
       if (phase == PH_ADAM) {
         bc1 = bias_corr(p.b1, R(gu + 1));
         bc2 = bias_corr(p.b2, R(gu + 1));
+        ibc1 = R(1) / bc1; ibc2 = R(1) / bc2;
       }
       for (int g = ls; g < p.n_su2; g += TPS) {
         const Su2Meta* md = p.su2 + g;
@@ -483,17 +484,17 @@ engine_kernel(const KParams<R> p) {
           const R C2 = c2 * c2 - s2 * s2, S2 = R(2) * c2 * s2;
           const R C3 = c3 * c3 - s3 * s3, S3 = R(2) * c3 * s3;
           if (pi2 >= 0)
-            apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi2, sel3(ax2, sx, sy, sz), th2);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi2, sel3(ax2, sx, sy, sz), th2);
           if (pi1 >= 0) {
             R x = ax1 == 0, y = ax1 == 1, z = ax1 == 2;
             rot_axis(ax2, C3, S3, x, y, z);
-            apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi1, x * sx + y * sy + z * sz, th1);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi1, x * sx + y * sy + z * sz, th1);
           }
           if (pi0 >= 0) {
             R x = ax0 == 0, y = ax0 == 1, z = ax0 == 2;
             rot_axis(ax1, C2, S2, x, y, z);
             rot_axis(ax2, C3, S3, x, y, z);
-            apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi0, x * sx + y * sy + z * sz, th0);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi0, x * sx + y * sy + z * sz, th0);
           }
         }
         if (!skip_coef) {
@@ -525,7 +526,7 @@ engine_kernel(const KParams<R> p) {
             penalty_eval_fast(p.pen, th, val, slope);
             g = add_rn(g, mul_rn(p.pen.r, slope));
           }
-          apply_grad(p, active, b, phase, gu, bc1, bc2, ang, mom, vel, frz, pi, g, th);
+          apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi, g, th);
         }
         if (!skip_coef) {
           R s = R(0), c = R(-1);                 // CZ = diag(1,1,1,-1) exactly
