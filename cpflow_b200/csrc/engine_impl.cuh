@@ -68,7 +68,7 @@ enum Phase : int { PH_COEF = 0, PH_ADAM = 1, PH_GRAD = 2 };
 template <typename R>
 __device__ __forceinline__ void apply_grad(const KParams<R>& p, bool active, long long b, int phase,
                                            long long gi, R bc1, R bc2, R ibc1, R ibc2, R* ang, R* mom, R* vel,
-                                           const uint8_t* frz, int pi, R g, R& th) {
+                                           const uint8_t* frz, int pi, R g, R& th, R mu0, R nu0) {
   const int P = p.P;
   if (phase == PH_GRAD) {
     if (active) p.grad_out[b * P + pi] = g;
@@ -76,8 +76,7 @@ __device__ __forceinline__ void apply_grad(const KParams<R>& p, bool active, lon
   }
   // a frozen parameter skips the Adam update only: its (unchanged) value still goes into the history row
   if (!(frz && frz[pi])) {
-    const R mu0 = gi == 0 ? R(0) : mom[pi];
-    const R nu0 = gi == 0 ? R(0) : vel[pi];
+    // (mu0, nu0: the moments before the step, loaded by the caller one gate ahead; zero for the first step)
     const AdamOut<R> o = adam_step_fused(g, th, mu0, nu0, p.b1, p.omb1, p.b2, p.omb2, bc1, bc2, ibc1, ibc2, p.eps, -p.lr);
     th = o.th;
     if (active) { mom[pi] = o.mu; vel[pi] = o.nu; ang[pi] = th; }
@@ -470,31 +469,52 @@ engine_kernel(const KParams<R> p) {
         bc2 = bias_corr(p.b2, R(gu + 1));
         ibc1 = R(1) / bc1; ibc2 = R(1) / bc2;
       }
+      // Software pipeline: the metadata, angles and Adam moments of the lane's NEXT gate are requested before the
+      // current one is processed (the loop was bound by these L2 round trips: long_scoreboard was the top stall).
+      struct PGate { int ax0, ax1, ax2, pi0, pi1, pi2; R th0, th1, th2, mu0, mu1, mu2, nu0, nu1, nu2; };
+      const bool want_mom = phase == PH_ADAM && gu != 0;
+      auto gate_load = [&](int g) {
+        PGate q{-1, -1, -1, -1, -1, -1, R(0), R(0), R(0), R(0), R(0), R(0), R(0), R(0), R(0)};
+        if (g < p.n_su2) {
+          const Su2Meta* md = p.su2 + g;
+          q.ax0 = md->axis[0]; q.ax1 = md->axis[1]; q.ax2 = md->axis[2];
+          q.pi0 = md->pidx[0]; q.pi1 = md->pidx[1]; q.pi2 = md->pidx[2];
+          q.th0 = q.pi0 >= 0 ? ang[q.pi0] : R(md->cangle[0]);
+          q.th1 = q.pi1 >= 0 ? ang[q.pi1] : R(md->cangle[1]);
+          q.th2 = q.pi2 >= 0 ? ang[q.pi2] : R(md->cangle[2]);
+          if (want_mom) {
+            if (q.pi0 >= 0) { q.mu0 = mom[q.pi0]; q.nu0 = vel[q.pi0]; }
+            if (q.pi1 >= 0) { q.mu1 = mom[q.pi1]; q.nu1 = vel[q.pi1]; }
+            if (q.pi2 >= 0) { q.mu2 = mom[q.pi2]; q.nu2 = vel[q.pi2]; }
+          }
+        }
+        return q;
+      };
+      PGate nxt = gate_load(ls);
       for (int g = ls; g < p.n_su2; g += TPS) {
-        const Su2Meta* md = p.su2 + g;
+        const PGate q = nxt;
+        nxt = gate_load(g + TPS);
         R* cf = coef + 8 * g;
-        const int ax0 = md->axis[0], ax1 = md->axis[1], ax2 = md->axis[2];
-        const int pi0 = md->pidx[0], pi1 = md->pidx[1], pi2 = md->pidx[2];
-        R th0 = pi0 >= 0 ? ang[pi0] : R(md->cangle[0]);
-        R th1 = pi1 >= 0 ? ang[pi1] : R(md->cangle[1]);
-        R th2 = pi2 >= 0 ? ang[pi2] : R(md->cangle[2]);
+        const int ax0 = q.ax0, ax1 = q.ax1, ax2 = q.ax2;
+        const int pi0 = q.pi0, pi1 = q.pi1, pi2 = q.pi2;
+        R th0 = q.th0, th1 = q.th1, th2 = q.th2;
         if (phase != PH_COEF) {
           const R sx = cf[0], sy = cf[1], sz = cf[2];
           const R c2 = cf[4], s2 = cf[5], c3 = cf[6], s3 = cf[7];
           const R C2 = c2 * c2 - s2 * s2, S2 = R(2) * c2 * s2;
           const R C3 = c3 * c3 - s3 * s3, S3 = R(2) * c3 * s3;
           if (pi2 >= 0)
-            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi2, sel3(ax2, sx, sy, sz), th2);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi2, sel3(ax2, sx, sy, sz), th2, q.mu2, q.nu2);
           if (pi1 >= 0) {
             R x = ax1 == 0, y = ax1 == 1, z = ax1 == 2;
             rot_axis(ax2, C3, S3, x, y, z);
-            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi1, x * sx + y * sy + z * sz, th1);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi1, x * sx + y * sy + z * sz, th1, q.mu1, q.nu1);
           }
           if (pi0 >= 0) {
             R x = ax0 == 0, y = ax0 == 1, z = ax0 == 2;
             rot_axis(ax1, C2, S2, x, y, z);
             rot_axis(ax2, C3, S3, x, y, z);
-            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi0, x * sx + y * sy + z * sz, th0);
+            apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi0, x * sx + y * sy + z * sz, th0, q.mu0, q.nu0);
           }
         }
         if (!skip_coef) {
@@ -526,7 +546,8 @@ engine_kernel(const KParams<R> p) {
             penalty_eval_fast(p.pen, th, val, slope);
             g = add_rn(g, mul_rn(p.pen.r, slope));
           }
-          apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi, g, th);
+          apply_grad(p, active, b, phase, gu, bc1, bc2, ibc1, ibc2, ang, mom, vel, frz, pi, g, th,
+                     want_mom ? mom[pi] : R(0), want_mom ? vel[pi] : R(0));
         }
         if (!skip_coef) {
           R s = R(0), c = R(-1);                 // CZ = diag(1,1,1,-1) exactly
