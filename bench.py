@@ -273,8 +273,8 @@ def static_wall_times():
 
 def other_rooflines(peak_tf, peak_detail):
     """Executed-flop rooflines and rates of the configurations next to the headline (BASELINE configs[3], [4]):
-    complex128 (FP64 FMA peak from tools/fp32_peak's DFMA chain), the 5-qubit templates, a run-time-pair layer
-    (HeisSweepAny), and the state-preparation / relative-phase losses on the state-adjoint kernels.  Short launches
+    complex128 (FP64 FMA peak from tools/fp32_peak's DFMA chain), the 5-qubit templates, the paper's kite layer, a layer
+    without a compile-time kernel (run-time pair dispatch, HeisSweepAny), and the state-preparation / relative-phase losses on the state-adjoint kernels.  Short launches
     (event-timed, second of two), not part of the headline."""
     import numpy as np
     import torch
@@ -290,7 +290,8 @@ def other_rooflines(peak_tf, peak_detail):
              ("C4_4q_chain_K40_complex128", 4, chain_layer(4), 40, torch.float64, "hs", 20000, 100),
              ("C5_5q_chain_K60_complex64", 5, chain_layer(5), 60, torch.float32, "hs", 40000, 100),
              ("C5_5q_connected_K60_complex64", 5, connected_layer(5), 60, torch.float32, "hs", 40000, 100),
-             ("toffoli4_kite_K25_complex64_anylayer", 4, [[0, 1], [1, 2], [2, 3], [1, 3]], 25, torch.float32, "hs", 100000, 200),
+             ("toffoli4_kite_K25_complex64", 4, [[0, 1], [1, 2], [2, 3], [1, 3]], 25, torch.float32, "hs", 100000, 200),
+             ("toffoli4_ring_K24_complex64_anylayer", 4, [[0, 1], [2, 3], [1, 2], [0, 3]], 24, torch.float32, "hs", 100000, 200),
              ("C5_5q_chain_K60_stateprep_complex64", 5, chain_layer(5), 60, torch.float32, "state", 200000, 100),
              ("C5_6q_chain_K60_stateprep_complex64", 6, chain_layer(6), 60, torch.float32, "state", 100000, 100),
              ("toffoli4_chain_K40_relphase_complex64", 4, chain_layer(4), 40, torch.float32, "relphase", 20000, 100)]
