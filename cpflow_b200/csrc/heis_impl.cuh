@@ -26,7 +26,7 @@
 //
 // Shared memory per sample: 8 words per fused gate + 3 per entangler + a staging area for the coefficients of
 // ONE layer of the backward sweep (produced just in time from the forward data), see HEIS_SU2_WORDS below.
-// Per sample and eval for C3 (n = 4, K = 40): ~5.6 k warp instructions (x 1/4 warp) instead of ~22 k.
+// Per sample and eval for C3 (n = 4, K = 40): ~4.9 k warp instructions (x 1/4 warp) instead of ~22 k.
 #pragma once
 #include <atomic>
 #include <cmath>
@@ -544,9 +544,9 @@ struct UpdCtx {
   R bc1, bc2, ibc1, ibc2;
 };
 
-// Optimiser state {theta, m, v, best} of a sample in the kernel's scratch, LANE-INTERLEAVED: the update phase is bound by
-// the L1 -> L2 request port (one 32-byte sector per cycle and SM), so the layout makes every access of a warp cover
-// whole sectors.  A parameter has a POSITION q (heis_pk_pos_*) chosen so that the parameters the lanes of a sample
+// Optimiser state {theta, m, v, best} of a sample in the kernel's scratch, LANE-INTERLEAVED: with one 16-byte record
+// per parameter the update phase was bound by the L1 -> L2 request port (one 32-byte sector per cycle and SM; every
+// access of a warp touched 16-32 half-used sectors), so the layout makes every access of a warp cover whole sectors.  A parameter has a POSITION q (heis_pk_pos_*) chosen so that the parameters the lanes of a sample
 // touch in the same instruction are neighbours; positions are stored in blocks of 16: word (q >> 4) * 64 + f * 16 +
 // (q & 15) holds field f (0 theta, 1 m, 2 v, 3 best-regloss parameter) of position q.  A fused gate g, rotation j:
 //   surface gates (g < n):      q = (j TPS + g) 2                                  (lane g, one gate per lane)
