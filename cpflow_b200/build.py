@@ -18,8 +18,12 @@ OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcpflow_b200.so")
 
+# (the Heisenberg kernels are spread over several translation units - tools/gen_heis_inst.py - because one nvcc per
+# source runs in parallel and a single file with all of them took four minutes)
 SOURCES = ["program.cpp", "inst_f32.cu", "inst_f64.cu", "inst_layer_f32.cu", "inst_layer_f64.cu",
-           "inst_heis_f32.cu", "inst_heis_f64.cu", "capi.cu"]
+           "inst_heis_f32.cu", "inst_heis_f64.cu",
+           "inst_heis_f32_p0.cu", "inst_heis_f32_p1.cu", "inst_heis_f32_p2.cu", "inst_heis_f32_p3.cu",
+           "inst_heis_f64_p0.cu", "inst_heis_f64_p1.cu", "inst_heis_f64_p2.cu", "inst_heis_f64_p3.cu", "capi.cu"]
 HEADERS = ["program.hpp", "engine.cuh", "engine_impl.cuh", "launch.cuh", "heis_impl.cuh",
            os.path.join(ROOT, "include", "cpflow_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -36,8 +36,13 @@ starts = [m[0] for m in marks]
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "inst_heis_f32", os.path.join(ROOT, "cpflow_b200", "lib", "libcpflow_b200.so")],
                    cwd=td, check=True, capture_output=True)
-    cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
-    sass = subprocess.run(["nvdisasm", "-gi", os.path.join(td, cub)], capture_output=True, text=True).stdout.split("\n")
+    # the kernels are spread over several translation units (inst_heis_f32_p*.cu): take the cubin that has this one
+    sass = []
+    for cub in sorted(f for f in os.listdir(td) if f.endswith(".cubin")):
+        txt = subprocess.run(["nvdisasm", "-gi", os.path.join(td, cub)], capture_output=True, text=True).stdout
+        if want in txt:
+            sass = txt.split("\n")
+            break
 ins = []   # (opcode text, kernel-body line)
 inside = False
 last_outer = None
