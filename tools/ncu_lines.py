@@ -7,14 +7,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, evals, phase = sys.argv[1], float(sys.argv[2]), sys.argv[3]
 kind = sys.argv[4] if len(sys.argv) > 4 else "nonfp"
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
-want = "heis_kernelIfLi4ELi2ENS_9HeisSweepIfLi4ELi2ELi3ELy528ELy801"
+want = os.environ.get("NCU_LINES_KERNEL", "heis_kernelIfLi4ELi2ENS_9HeisSweepIfLi4ELi2ELi3ELy528ELy801")
 src = open(os.path.join(ROOT, "cpflow_b200", "csrc", "heis_impl.cuh")).read().split("\n")
 def find(txt):
     return next(i + 1 for i, l in enumerate(src) if txt in l)
 lo = {"update": find("for (int it = 0; it <= p.nsteps"), "forward": find("V yr[N], yi[N];"), "backward": find("SWP::backward(p, lb")}[phase]
 hi = {"update": find("V yr[N], yi[N];"), "forward": find("SWP::gather_wht(yr, yi)"), "backward": find("if (p.mode == M_ADAM && active) {\n") if False else lo + 1}[phase]
 with tempfile.TemporaryDirectory() as td:
-    subprocess.run(["cuobjdump", "-xelf", "inst_heis_f32", os.path.join(ROOT, "cpflow_b200", "lib", "libcpflow_b200.so")],
+    subprocess.run(["cuobjdump", "-xelf", os.environ.get("NCU_REGIONS_CUBIN", "inst_heis_f32"), os.path.join(ROOT, "cpflow_b200", "lib", "libcpflow_b200.so")],
                    cwd=td, check=True, capture_output=True)
     # the kernels are spread over several translation units (inst_heis_f32_p*.cu): take the cubin that has this one
     sass = []

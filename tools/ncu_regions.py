@@ -34,7 +34,7 @@ starts = [m[0] for m in marks]
 
 # ---- line table of the kernel ----
 with tempfile.TemporaryDirectory() as td:
-    subprocess.run(["cuobjdump", "-xelf", "inst_heis_f32", os.path.join(ROOT, "cpflow_b200", "lib", "libcpflow_b200.so")],
+    subprocess.run(["cuobjdump", "-xelf", os.environ.get("NCU_REGIONS_CUBIN", "inst_heis_f32"), os.path.join(ROOT, "cpflow_b200", "lib", "libcpflow_b200.so")],
                    cwd=td, check=True, capture_output=True)
     # the kernels are spread over several translation units (inst_heis_f32_p*.cu): take the cubin that has this one
     sass = []
